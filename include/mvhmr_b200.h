@@ -1,0 +1,161 @@
+/*
+ * mvhmr_b200.h — C ABI of the B200-native volumetric-aggregation path.
+ *
+ * This is the drop-in boundary for MultiviewHMR's aggregation hot path
+ * (SURVEY.md §8(b)).  The reference has no FFI: its boundary is the Python
+ * import of models/aggregation.py, utils/volumetric.py and utils/multiview.py.
+ * Every entry point below replaces the torch-op sequence of one reference
+ * function (cited per declaration, paths relative to /root/reference) and is
+ * what a ctypes/cffi binding on the reference side would bind — see
+ * INTEGRATION.md for the stub.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only.  All `const float*` / `void*` data
+ *     pointers are DEVICE pointers on the current CUDA device unless a
+ *     parameter says "host".  The caller owns every buffer; the library
+ *     allocates nothing and keeps no state between calls.
+ *   - Every call is asynchronous on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream), does no host synchronisation and
+ *     no allocation, and is CUDA-graph capturable.
+ *   - Return value: MVHMR_OK or a negative MVHMR_ERR_*.  The message of the
+ *     last failure on the calling thread is available from
+ *     mvhmr_last_error().  The library never aborts and never prints.
+ *   - Re-entrant: safe to call concurrently from several host threads.
+ *   - fp32 results follow the reference's rounding order op for op
+ *     (sum / mean / max fusion and all grids are bit-identical to the
+ *     reference's CPU torch path; softmax differs only by the exp
+ *     approximation, ~1e-7 relative).
+ */
+#ifndef MVHMR_B200_H
+#define MVHMR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVHMR_ABI_VERSION 1
+
+/* return codes */
+#define MVHMR_OK 0
+#define MVHMR_ERR_INVALID_ARGUMENT (-1) /* maps to ValueError on the Python side */
+#define MVHMR_ERR_WORKSPACE (-2)        /* workspace missing or too small        */
+#define MVHMR_ERR_CUDA (-3)             /* a CUDA runtime call failed            */
+
+/* aggregation_method of models/aggregation.py:71-85 */
+#define MVHMR_SUM 0
+#define MVHMR_MEAN 1
+#define MVHMR_MAX 2
+#define MVHMR_SOFTMAX 3
+
+/* storage type of the feature maps */
+#define MVHMR_F32 0
+#define MVHMR_BF16 1
+
+/* layout of the feature maps handed to mvhmr_unproject_aggregate */
+#define MVHMR_LAYOUT_NCHW 0   /* (B,V,C,H,W) as the reference passes them      */
+#define MVHMR_LAYOUT_PACKED 1 /* already in the library's gather layout, i.e.  */
+                              /* the output of mvhmr_pack_features             */
+
+int mvhmr_abi_version(void);
+
+/* Message of the last error on this thread ("" if none).  Never NULL. */
+const char *mvhmr_last_error(void);
+
+/* ---- grids -------------------------------------------------------------- */
+
+/* Per-sample cuboid coordinate volume.
+ * Replaces models/aggregation.py:135-161 (grid build), :184-187 (centre,
+ * rotate, un-centre) and utils/volumetric.py:102-114 (rotate_coord_volume):
+ *   out[b,x,y,z,:] = rot[b] · ((pos + step*idx) - centers[b]) + centers[b]
+ * with the reference's fp32 roundings (separate mul and add; K=3 FMA chain).
+ * out (B,Gx,Gy,Gz,3); centers (B,3); rot (B,3,3) row-major, identity in eval;
+ * pos_host / step_host: 3 floats each in HOST memory (pos = -side/2,
+ * step = side/(G-1), already rounded to fp32). */
+int mvhmr_build_coord_volumes(float *out, const float *centers, const float *rot,
+                              const float *pos_host, const float *step_host,
+                              int B, int Gx, int Gy, int Gz, void *stream);
+
+/* utils/volumetric.py:102-114 on an arbitrary (N,3) point array:
+ * out[n,:] = rot · pts[n,:].  rot_host: 9 floats, row-major, HOST memory.
+ * out may alias pts. */
+int mvhmr_rotate_points(float *out, const float *pts, const float *rot_host, size_t N, void *stream);
+
+/* utils/multiview.py:89-110 for torch inputs: out = [pts 1] · P^T, fp32 K=4 FMA
+ * chain.  P (3,4) device.  euclid=0: out (N,3) homogeneous (x*w, y*w, w);
+ * euclid=1: out (N,2) after utils/multiview.py:72-86 (division by w; w == 0
+ * divides by zero exactly as the reference does). */
+int mvhmr_project_points(float *out, const float *P, const float *pts, size_t N, int euclid, void *stream);
+
+/* ---- unproject + aggregate ---------------------------------------------- */
+
+/* Bytes of the packed gather layout for BV = B*V feature maps (0 on bad args). */
+size_t mvhmr_packed_bytes(int feat_dtype, int BV, int C, int H, int W);
+
+/* NCHW (BV,C,H,W) -> packed gather layout: channel vectors of 16 bytes
+ * (4 x fp32 / 8 x bf16) per texel, planes padded by a 2-texel zero border so
+ * that out-of-map corners read zeros (grid_sample padding_mode='zeros'). */
+int mvhmr_pack_features(const void *feats, int feat_dtype, void *packed,
+                        int BV, int C, int H, int W, void *stream);
+
+/* Workspace needed by mvhmr_unproject_aggregate for the given layout
+ * (= mvhmr_packed_bytes for NCHW input, 0 for PACKED input). */
+size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, int V, int C, int H, int W);
+
+/* Fused replacement of models/aggregation.py:20-87 `unprojection`:
+ * project every voxel centre with each view's 3x4 matrix, bilinear-sample the
+ * view's feature map (align_corners=True, zeros padding, x normalised by H and
+ * y by W as the reference does), zero samples with depth <= 0, fuse over views.
+ *   feats  (B,V,C,H,W) [NCHW] or packed; feat_dtype fp32 / bf16
+ *   proj   (B,V,3,4) fp32
+ *   coord  (B,n_extent,3) fp32 and out (B,C,n_extent) fp32 hold voxels
+ *          [n_origin, n_origin+n_extent) of the flattened N = gx*gy*gz voxel
+ *          volume (pass 0,N for whole-volume buffers; a slab shard may pass
+ *          compact buffers covering only its slab)
+ *   method MVHMR_SUM / MEAN / MAX / SOFTMAX
+ *   [b0,b1) x [n0,n1): shard window — only these samples / voxels are computed
+ *   and written (pass 0,B,0,N for everything).  Slab and batch shards of one
+ *   problem are bit-identical to the unsharded call.
+ *   tile_hint: 0 = automatic; otherwise TX | TY<<8 | TZ<<16, the voxel brick of
+ *   one 256-thread CTA over a (Gx,Gy,Gz) volume (requires gx*gy*gz == N).
+ *   ws / ws_bytes: caller workspace (see mvhmr_unproject_workspace_bytes).
+ * gx,gy,gz: volume shape; used only for brick tiling, any factorisation with
+ * gx*gy*gz == N is legal. */
+int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int feat_layout,
+                              const float *proj, const float *coord, float *out,
+                              int B, int V, int C, int H, int W,
+                              int gx, int gy, int gz, int method,
+                              int b0, int b1, long long n0, long long n1,
+                              long long n_origin, long long n_extent,
+                              unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
+
+/* ---- 3-D soft-argmax ------------------------------------------------------ */
+/* Not in the reference; upstream definition
+ * (Learnable-Triangulation integrate_tensor_3d_with_coordinates, cited by URL at
+ * models/aggregation.py:13-17):
+ *   p = softmax(vol[b,j,:]);  out[b,j,:] = sum_n p[n] * coord[b,n,:]        */
+
+/* Number of (max, sum_e, sum_e*x, sum_e*y, sum_e*z) partial records per (b,j)
+ * that mvhmr_soft_argmax3d_partials writes for N voxels. */
+int mvhmr_soft_argmax3d_num_slices(long long N);
+
+size_t mvhmr_soft_argmax3d_workspace_bytes(int B, int J, long long N);
+
+/* One-call form: vol (B,J,N), coord (B,N,3) -> out (B,J,3). */
+int mvhmr_soft_argmax3d(const float *vol, const float *coord, float *out,
+                        int B, int J, long long N, void *ws, size_t ws_bytes, void *stream);
+
+/* Shard form.  partials: (B,J,S,5) with S = num_slices(n1-n0), over voxels
+ * [n0,n1) of each sample; vol / coord are indexed with the FULL N. */
+int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord, float *partials,
+                                 int B, int J, long long N, long long n0, long long n1, void *stream);
+
+/* Merge S records per (b,j) (from one or several shards, concatenated along S)
+ * into out (B,J,3). */
+int mvhmr_soft_argmax3d_finalize(const float *partials, float *out, int B, int J, int S, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVHMR_B200_H */

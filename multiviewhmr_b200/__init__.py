@@ -1,0 +1,19 @@
+"""multiviewhmr_b200 — B200-native (sm_100a) volumetric aggregation for
+multi-view human mesh recovery.
+
+Host-side mirror of the three reference modules on the aggregation hot path:
+
+    multiviewhmr_b200.aggregation  <->  models/aggregation.py
+    multiviewhmr_b200.volumetric   <->  utils/volumetric.py
+    multiviewhmr_b200.multiview    <->  utils/multiview.py
+
+backed by hand-written CUDA kernels behind the C ABI in include/mvhmr_b200.h.
+`multiviewhmr_b200.dropin.install()` registers them under the reference's
+module names.
+"""
+from . import aggregation, multiview, volumetric  # noqa: F401
+from .aggregation import (VolumeGenerator, build_volume_generator, pack_features,  # noqa: F401
+                          soft_argmax_3d, unprojection)
+
+__all__ = ["aggregation", "multiview", "volumetric", "unprojection", "VolumeGenerator",
+           "build_volume_generator", "soft_argmax_3d", "pack_features"]

@@ -1,0 +1,293 @@
+"""Drop-in for the reference's `models/aggregation.py`.
+
+Same call signatures, same results, one fused sm_100a kernel instead of the
+per-view `F.grid_sample` loop:
+
+    unprojection(features, proj_matricies, coord_volumes, aggregation_method)
+    VolumeGenerator(...).forward(features, proj_matricies, batch, use_gt=True)
+    build_volume_generator(cfg)
+    soft_argmax_3d(volumes, coord_volumes)          # new: not in the reference
+
+All tensors must be CUDA tensors; the library behind `_lib` is the only
+implementation (no eager fallback).
+"""
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, multiview, volumetric
+
+_AXES = {"coco": [0, 1, 0], "mpii": [0, 0, 1]}     # models/aggregation.py:169-172
+
+
+def _tile_hint():
+    """MVHMR_TILE="TX,TY,TZ" overrides the CTA voxel brick (tuning knob)."""
+    spec = os.environ.get("MVHMR_TILE")
+    if not spec:
+        return 0
+    tx, ty, tz = (int(v) for v in spec.split(","))
+    return tx | (ty << 8) | (tz << 16)
+
+
+def _feat_dtype(features):
+    if features.dtype == torch.float32:
+        return _lib.F32
+    if features.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise TypeError("multiviewhmr_b200: feature maps must be float32 or bfloat16, got %s" % features.dtype)
+
+
+def pack_features(features):
+    """(B,V,C,H,W) -> the library's gather layout (opaque uint8 tensor).
+    Lets a caller that reuses one set of feature maps for several grids pay the
+    layout pass once (`unprojection(..., packed=...)`)."""
+    dev = _lib.require_cuda(features)
+    B, V, C, H, W = features.shape
+    dt = _feat_dtype(features)
+    L = _lib.load()
+    packed = torch.empty(L.mvhmr_packed_bytes(dt, B * V, C, H, W), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.mvhmr_pack_features(_lib.ptr(features.contiguous()), dt, _lib.ptr(packed),
+                                         B * V, C, H, W, _lib.stream_ptr(dev)))
+    return packed
+
+
+def unprojection(features, proj_matricies, coord_volumes, aggregation_method='softmax',
+                 window=None, out=None, packed=None):
+    """Unproject V feature maps into the voxel grid and fuse over views.
+
+    Reference: `models/aggregation.py:20-87`.
+      features        (B, V, C, H, W)  float32 or bfloat16, CUDA
+      proj_matricies  (B, V, 3, 4)
+      coord_volumes   (B, Gx, Gy, Gz, 3)
+      aggregation_method  'sum' | 'mean' | 'max' | 'softmax'
+    Returns (B, C, Gx, Gy, Gz) float32 on `features.device` (the reference's
+    `volume_batch` is fp32 whatever the feature dtype, `:25`).
+
+    Extras (not in the reference): `window=(b0, b1, n0, n1)` computes only a
+    shard of samples / flattened voxels into `out`; `packed` re-uses a
+    `pack_features` result.
+    """
+    if aggregation_method not in _lib.METHODS:
+        raise ValueError("Unknown aggregation_method: {}".format(aggregation_method))
+    dev = _lib.require_cuda(features, proj_matricies, coord_volumes)
+    if features.dim() != 5 or coord_volumes.dim() != 5 or coord_volumes.shape[-1] != 3:
+        raise ValueError("expected features (B,V,C,H,W) and coord_volumes (B,Gx,Gy,Gz,3), got %s and %s"
+                         % (tuple(features.shape), tuple(coord_volumes.shape)))
+    B, V, C, H, W = features.shape
+    if tuple(proj_matricies.shape) != (B, V, 3, 4) or coord_volumes.shape[0] != B:
+        raise ValueError("shape mismatch: features %s, proj_matricies %s, coord_volumes %s"
+                         % (tuple(features.shape), tuple(proj_matricies.shape), tuple(coord_volumes.shape)))
+    if torch.is_grad_enabled() and features.requires_grad:
+        from .autograd import unprojection_with_grad
+        return unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method)
+    gx, gy, gz = (int(v) for v in coord_volumes.shape[1:4])
+    N = gx * gy * gz
+    dt = _feat_dtype(features)
+    L = _lib.load()
+    proj = proj_matricies.detach().float().contiguous()
+    coord = coord_volumes.detach().float().contiguous()
+    if out is None:
+        out = torch.empty((B, C, gx, gy, gz), dtype=torch.float32, device=dev)
+    elif (tuple(out.shape) != (B, C, gx, gy, gz) or out.dtype != torch.float32
+          or not out.is_contiguous() or out.device != dev):
+        raise ValueError("out must be a contiguous float32 (B,C,Gx,Gy,Gz) tensor on %s" % dev)
+    b0, b1, n0, n1 = (0, B, 0, N) if window is None else (int(v) for v in window)
+    with torch.cuda.device(dev):
+        if packed is None:
+            feats = features.detach().contiguous()
+            layout = _lib.LAYOUT_NCHW
+            ws_bytes = L.mvhmr_unproject_workspace_bytes(dt, layout, B, V, C, H, W)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws_ptr = _lib.ptr(ws)
+        else:
+            feats, layout, ws_bytes, ws_ptr = packed, _lib.LAYOUT_PACKED, 0, None
+            if packed.numel() != L.mvhmr_packed_bytes(dt, B * V, C, H, W):
+                raise ValueError("packed features do not match the shape of `features`")
+        _lib.check(L.mvhmr_unproject_aggregate(
+            _lib.ptr(feats), dt, layout, _lib.ptr(proj), _lib.ptr(coord), _lib.ptr(out),
+            B, V, C, H, W, gx, gy, gz, _lib.METHODS[aggregation_method],
+            b0, b1, n0, n1, 0, N, _tile_hint(), ws_ptr, ws_bytes, _lib.stream_ptr(dev)))
+    return out
+
+
+def soft_argmax_3d(volumes, coord_volumes):
+    """Per-joint 3-D soft-argmax: softmax over all voxels of `volumes[b, j]`,
+    expectation of `coord_volumes[b]`.  (B,J,Gx,Gy,Gz) x (B,Gx,Gy,Gz,3) -> (B,J,3).
+
+    Not part of the reference; the formula is upstream
+    Learnable-Triangulation's `integrate_tensor_3d_with_coordinates`."""
+    dev = _lib.require_cuda(volumes, coord_volumes)
+    if volumes.dim() != 5 or coord_volumes.dim() != 5 or coord_volumes.shape[-1] != 3 \
+            or tuple(volumes.shape[2:]) != tuple(coord_volumes.shape[1:4]) \
+            or volumes.shape[0] != coord_volumes.shape[0]:
+        raise ValueError("expected volumes (B,J,Gx,Gy,Gz) and coord_volumes (B,Gx,Gy,Gz,3), got %s and %s"
+                         % (tuple(volumes.shape), tuple(coord_volumes.shape)))
+    if volumes.dtype != torch.float32:
+        raise TypeError("multiviewhmr_b200: soft_argmax_3d takes float32 volumes, got %s" % volumes.dtype)
+    B, J = volumes.shape[:2]
+    N = int(np.prod(volumes.shape[2:]))
+    L = _lib.load()
+    vol = volumes.detach().contiguous()
+    coord = coord_volumes.detach().float().contiguous()
+    out = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    ws_bytes = L.mvhmr_soft_argmax3d_workspace_bytes(B, J, N)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.mvhmr_soft_argmax3d(_lib.ptr(vol), _lib.ptr(coord), _lib.ptr(out), B, J, N,
+                                         _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+    return out
+
+
+def soft_argmax_3d_records(volumes, coord_volumes):
+    """Shard form of `soft_argmax_3d`: online-softmax records (B,J,S,5) =
+    (max, sum e, sum e*x, sum e*y, sum e*z) over the voxels of the tensors
+    given (a whole volume or one rank's x-slab).  Records of several shards are
+    concatenated along S and finished by `soft_argmax_3d_from_records`."""
+    dev = _lib.require_cuda(volumes, coord_volumes)
+    if volumes.dtype != torch.float32:
+        raise TypeError("multiviewhmr_b200: soft_argmax_3d takes float32 volumes, got %s" % volumes.dtype)
+    B, J = volumes.shape[:2]
+    N = int(np.prod(volumes.shape[2:]))
+    if coord_volumes.numel() != B * N * 3:
+        raise ValueError("coord_volumes %s does not match volumes %s"
+                         % (tuple(coord_volumes.shape), tuple(volumes.shape)))
+    L = _lib.load()
+    S = L.mvhmr_soft_argmax3d_num_slices(N)
+    rec = torch.empty((B, J, S, 5), dtype=torch.float32, device=dev)
+    vol = volumes.detach().contiguous()
+    coord = coord_volumes.detach().float().contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(L.mvhmr_soft_argmax3d_partials(_lib.ptr(vol), _lib.ptr(coord), _lib.ptr(rec),
+                                                  B, J, N, 0, N, _lib.stream_ptr(dev)))
+    return rec
+
+
+def soft_argmax_3d_from_records(records):
+    """(B,J,S,5) records -> (B,J,3)."""
+    dev = _lib.require_cuda(records)
+    B, J, S, five = records.shape
+    if five != 5 or records.dtype != torch.float32:
+        raise ValueError("records must be float32 (B,J,S,5)")
+    rec = records.contiguous()
+    out = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().mvhmr_soft_argmax3d_finalize(_lib.ptr(rec), _lib.ptr(out), B, J, S,
+                                                            _lib.stream_ptr(dev)))
+    return out
+
+
+def build_coord_volumes(centers, rotations, volume_size, cuboid_side, device):
+    """GPU build of the per-sample coord volumes, `models/aggregation.py:135-187`.
+
+    centers (B,3) and rotations (B,3,3): host float32 arrays.  One H2D copy of
+    B*12 floats, one kernel; the result is bit-identical to the reference's
+    meshgrid / affine / mm sequence."""
+    centers = np.ascontiguousarray(centers, dtype=np.float32)
+    rotations = np.ascontiguousarray(rotations, dtype=np.float32)
+    B = centers.shape[0]
+    G = int(volume_size)
+    # position = base_point - sides/2 with base_point (0,0,0); python floats are
+    # cast to fp32 by torch when they meet the fp32 grid (`:156-158`)
+    pos = np.float32(0.0 - cuboid_side / 2)
+    step = np.float32(cuboid_side / (G - 1))
+    host = torch.from_numpy(np.concatenate([centers.reshape(B, 3), rotations.reshape(B, 9)], axis=1))
+    dev_buf = host.to(device)
+    out = torch.empty((B, G, G, G, 3), dtype=torch.float32, device=device)
+    cen, rot = dev_buf[:, :3].contiguous(), dev_buf[:, 3:].contiguous()
+    with torch.cuda.device(device):
+        _lib.check(_lib.load().mvhmr_build_coord_volumes(
+            _lib.ptr(out), _lib.ptr(cen), _lib.ptr(rot), _lib.host3([pos] * 3), _lib.host3([step] * 3),
+            B, G, G, G, _lib.stream_ptr(out.device)))
+    return out
+
+
+class VolumeGenerator(nn.Module):
+    """Reference `models/aggregation.py:90-195`: camera rescale, per-sample
+    coord volume, 1x1 channel squeeze, unprojection.  `state_dict` keys are the
+    reference's (`process_feature.0.weight`, `process_feature.0.bias`)."""
+
+    def __init__(self,
+                 volume_size=64,
+                 input_channels=256,
+                 output_channels=32,
+                 cuboid_side=2500.0,
+                 aggregation_method='softmax',
+                 use_triangulation=False,
+                 kind='mpii',
+                 device='cuda',
+                 dataset='human36m',
+                 **kwargs):
+        super().__init__()
+        self.volume_size = volume_size
+        self.cuboid_side = cuboid_side
+        self.aggregation_method = aggregation_method
+        self.process_feature = nn.Sequential(nn.Conv2d(input_channels, output_channels, 1))
+        self.use_triangulation = use_triangulation
+        self.kind = kind
+        self.dataset = dataset
+        self.to(device)
+
+    def _projections(self, batch, images_shape, features_shape, n_views, batch_size):
+        """`:127-133`: K rescaled from image to feature-map size, P = K·[R|t] in
+        float64, then cast to fp32.  Returns a (B,V,3,4) float32 host array."""
+        P = np.empty((batch_size, n_views, 3, 4), dtype=np.float32)
+        for v in range(n_views):
+            for b in range(batch_size):
+                src = batch['cameras'][v][b]
+                cam = multiview.Camera(src.R, src.t, src.K)      # private copy, like the reference's deepcopy
+                cam.update_after_resize(images_shape, features_shape)
+                P[b, v] = cam.projection
+        return P
+
+    def forward(self, features, proj_matricies, batch, use_gt=True):
+        device = features.device
+        _lib.require_cuda(features)
+        features_shape = tuple(features.shape[-2:])
+        images_shape = tuple(batch['images'].shape[2:-1])
+        batch_size, n_views = batch['images'].shape[:2]
+        if self.kind not in _AXES:
+            raise ValueError("VolumeGenerator.kind must be 'coco' or 'mpii', got %r" % (self.kind,))
+        axis = _AXES[self.kind]
+
+        proj = torch.from_numpy(self._projections(batch, images_shape, features_shape, n_views, batch_size)).to(device)
+
+        centers = np.empty((batch_size, 3), dtype=np.float32)
+        rots = np.empty((batch_size, 3, 3), dtype=np.float32)
+        proj_org = proj_matricies.detach().float().cpu() if self.use_triangulation else None
+        for b in range(batch_size):
+            theta = np.random.uniform(0.0, 2 * np.pi) if self.training else 0.0   # `:164-167`
+            rots[b] = volumetric.get_rotation_matrix(axis, theta)
+            if self.use_triangulation:
+                # `:174-177`; the 2V x 4 SVD runs on the host so the centre does not
+                # depend on the cuSOLVER build
+                images_center = (torch.tensor(images_shape) / 2).expand(n_views, 2)
+                centers[b] = multiview.triangulate_point_from_multiple_views_linear_torch(
+                    proj_org[b], images_center).numpy()
+            else:
+                centers[b] = np.asarray(batch['keypoints_3d'][b])[6, :3]          # `:180-181`
+        coord_volumes = build_coord_volumes(centers, rots, self.volume_size, self.cuboid_side, device)
+
+        features = features.view(-1, *features.shape[2:])
+        features = self.process_feature(features)
+        features = features.view(batch_size, n_views, *features.shape[1:])
+
+        return unprojection(features, proj, coord_volumes, aggregation_method=self.aggregation_method)
+
+
+def build_volume_generator(cfg):
+    """Reference `models/aggregation.py:198-208`.  The reference passes the cfg
+    method as `volume_aggregation_method=`, which `VolumeGenerator.__init__`
+    swallows in **kwargs, so the module always fuses with 'softmax'
+    (SURVEY.md §0 fact 4).  Kept: a drop-in must not change model outputs."""
+    input_channels = cfg.MODEL.BACKBONE.DECONV_FILTERS[-1] if cfg.MODEL.BACKBONE.DECONV_LAYERS != 0 else 2048
+    return VolumeGenerator(volume_size=cfg.MODEL.AGGREGATION.VOLUME_SIZE,
+                           input_channels=input_channels,
+                           output_channels=cfg.MODEL.AGGREGATION.OUTPUT_CHANNELS,
+                           cuboid_side=cfg.MODEL.AGGREGATION.CUBOID_SIDE,
+                           use_triangulation=cfg.MODEL.AGGREGATION.USE_TRIANGULATION,
+                           kind=cfg.DATASET.KIND,
+                           dataset=cfg.DATASET.TYPE,
+                           volume_aggregation_method=cfg.MODEL.AGGREGATION.METHOD)

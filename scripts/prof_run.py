@@ -1,0 +1,21 @@
+"""Tiny driver for ncu captures: one workload, a few launches of the hot path."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multiviewhmr_b200 import synthetic as syn, aggregation as agg
+
+name = sys.argv[1] if len(sys.argv) > 1 else 'cfg2'
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+w = syn.CONFIGS[name]
+dev = torch.device('cuda:0')
+f, P, cv, c = syn.make_inputs(w)
+fd, Pd, cvd = f.to(dev), P.to(dev), cv.to(dev)
+if w.dtype == 'bf16':
+    fd = fd.bfloat16()
+out = torch.empty((w.B, w.C, w.G, w.G, w.G), device=dev)
+for _ in range(iters):
+    agg.unprojection(fd, Pd, cvd, w.method, out=out)
+    if w.joints:
+        agg.soft_argmax_3d(out[:, :w.joints].contiguous(), cvd)
+torch.cuda.synchronize()
+print('done', float(out.sum()))
