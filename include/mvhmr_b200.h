@@ -93,9 +93,10 @@ int mvhmr_project_points(float *out, const float *P, const float *pts, size_t N,
 /* Bytes of the packed gather layout for BV = B*V feature maps (0 on bad args). */
 size_t mvhmr_packed_bytes(int feat_dtype, int BV, int C, int H, int W);
 
-/* NCHW (BV,C,H,W) -> packed gather layout: channel vectors of 16 bytes
- * (4 x fp32 / 8 x bf16) per texel, planes padded by a 2-texel zero border so
- * that out-of-map corners read zeros (grid_sample padding_mode='zeros'). */
+/* NCHW (BV,C,H,W) -> packed gather layout: pixel-major planes (all channels of
+ * a pixel contiguous, padded to a power-of-two number of 16-byte vectors),
+ * each plane surrounded by a 2-texel zero border so that out-of-map corners
+ * read zeros (grid_sample padding_mode='zeros'). */
 int mvhmr_pack_features(const void *feats, int feat_dtype, void *packed,
                         int BV, int C, int H, int W, void *stream);
 
@@ -117,11 +118,11 @@ size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, i
  *   [b0,b1) x [n0,n1): shard window — only these samples / voxels are computed
  *   and written (pass 0,B,0,N for everything).  Slab and batch shards of one
  *   problem are bit-identical to the unsharded call.
- *   tile_hint: 0 = automatic; otherwise TX | TY<<8 | TZ<<16, the voxel brick of
- *   one 256-thread CTA over a (Gx,Gy,Gz) volume (requires gx*gy*gz == N).
+ *   tile_hint: 0 = automatic; otherwise the number of consecutive z voxels
+ *   (<= 64) one warp walks per task (tuning knob; results do not depend on it).
  *   ws / ws_bytes: caller workspace (see mvhmr_unproject_workspace_bytes).
- * gx,gy,gz: volume shape; used only for brick tiling, any factorisation with
- * gx*gy*gz == N is legal. */
+ * gx,gy,gz: volume shape; used only to cut the volume into z runs, any
+ * factorisation with gx*gy*gz == N is legal. */
 int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int feat_layout,
                               const float *proj, const float *coord, float *out,
                               int B, int V, int C, int H, int W,

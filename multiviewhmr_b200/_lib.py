@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libmvhmr_b200.so")
+LIB_PATH = os.environ.get("MVHMR_LIB") or os.path.join(_HERE, "lib", "libmvhmr_b200.so")   # MVHMR_LIB: tuning builds
 
 OK, ERR_INVALID_ARGUMENT, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3
 SUM, MEAN, MAX, SOFTMAX = 0, 1, 2, 3

@@ -23,12 +23,9 @@ _AXES = {"coco": [0, 1, 0], "mpii": [0, 0, 1]}     # models/aggregation.py:169-1
 
 
 def _tile_hint():
-    """MVHMR_TILE="TX,TY,TZ" overrides the CTA voxel brick (tuning knob)."""
-    spec = os.environ.get("MVHMR_TILE")
-    if not spec:
-        return 0
-    tx, ty, tz = (int(v) for v in spec.split(","))
-    return tx | (ty << 8) | (tz << 16)
+    """MVHMR_LZ=<n> overrides the z-segment length of one warp task (tuning knob)."""
+    spec = os.environ.get("MVHMR_LZ")
+    return int(spec) if spec else 0
 
 
 def _feat_dtype(features):

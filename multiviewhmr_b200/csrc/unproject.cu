@@ -1,83 +1,166 @@
 // Fused unproject + aggregate (models/aggregation.py:20-87) for sm_100a.
 //
-// Data layout in HBM
-//   features arrive NCHW (B,V,C,H,W).  pack_kernel rewrites them once into the
-//   gather layout  (B*V, chunks, H+4, W+4) x 16-byte texels, a texel holding 4
-//   fp32 (or 8 bf16) consecutive channels of one pixel, each plane surrounded
-//   by a 2-texel ZERO border.  With the border, grid_sample's zeros padding is
-//   just a clamp of the cell index: no per-corner predicate, no divergent code.
-//   Neighbouring pixels are neighbouring 16-byte words, so the 32 lanes of a
-//   warp (32 consecutive voxels along z, which project to a short run of
-//   pixels) read a handful of 128-byte lines per LDG.128.
+// Why this shape.  Per voxel-channel-view the op needs 4 texels (16 B fp32) out of
+// L1 but only ~1.2 B out of HBM, so the first walls are the SM's L1 data pipe
+// (one 128-byte wavefront per clock), the MUFU unit (one exp per
+// voxel-channel-view) and plain instruction issue — not HBM.  The kernel is
+// organised to spend as few wavefronts, MUFU ops and issue slots per sample as
+// possible:
 //
-// unproject_kernel: one thread per voxel, all views, all channels.
-//   1. project the voxel with every view's matrix (IEEE ops in the reference's
-//      order, so the sampling position is bit-identical to the CPU torch path),
-//      keep (texel offset, 4 weights) per view in registers;
-//   2. for each group of 8 channels: gather 4 corners x views (all loads are
-//      independent -> deep MLP), blend with one mul + three FMAs (== ATen),
-//      fuse over views in registers (sum / mean / max / softmax) and write the
-//      8 results with one coalesced 128-byte line per channel per warp.
-//   No per-view volume is ever materialised; HBM sees the features once (they
-//   stay L2-resident, 126 MB), the coordinates once and the output once.
+//   * Gather layout (pack_kernel): pixel-major planes, all channels of a pixel
+//     contiguous (128 B for 32 fp32 channels), planes padded by a 2-texel ZERO
+//     border so grid_sample's zeros padding is a clamp of the cell index.
+//   * A voxel is served by a GROUP of lanes, one 16-byte channel vector each
+//     (8 lanes for 32 fp32 channels): a group's load of one corner is exactly
+//     one aligned 128-byte line = one L1 wavefront, whatever the camera looks
+//     like.  A warp holds 32/LPV groups; each group WALKS a run of consecutive z
+//     voxels and keeps the four corner texels of every view in registers: when
+//     the next voxel projects into the same bilinear cell (views looking along
+//     z move ~0.3 px per voxel) nothing is loaded at all.
+//   * Phase A (once per warp task = one z segment of <= 64 voxels): every lane
+//     projects up to two voxels through every view with IEEE ops in the
+//     reference's order and parks (pixel offset, 4 weights) in shared memory,
+//     so the projection is never recomputed per channel.  Phase B: the walk.
+//     Blend = mul + 3 FMA per channel issued as packed FFMA2; view fusion in
+//     registers (softmax: one FFMA2 for two exp arguments, MUFU.EX2).
+//   * Results are transposed through a swizzled shared-memory tile so that each
+//     warp writes full 128-byte lines of the (B,C,N) output; every output value
+//     is written exactly once and no per-view volume exists anywhere.
 #include <cuda_bf16.h>
 #include "mvhmr_common.cuh"
 
 namespace mvhmr {
 
 constexpr int kBorder = 2;
-constexpr int kBlock = 256;
-constexpr int kGroupCh = 8;            // channels fused per inner iteration
+#ifndef MVHMR_WARPS
+#define MVHMR_WARPS 16
+#endif
+#ifndef MVHMR_MINBLOCKS
+#define MVHMR_MINBLOCKS 1
+#endif
+#ifndef MVHMR_CACHE4
+#define MVHMR_CACHE4 true
+#endif
+#ifndef MVHMR_LZCAP
+#define MVHMR_LZCAP 32
+#endif
+constexpr int kWarps = MVHMR_WARPS;       // warps per CTA: consecutive x planes share their texel footprint in L1
+constexpr int kLzMax = 32;                // voxels of one warp task (z segment): one per lane in phase A
+constexpr int kVecPass = 32;              // 16-byte channel vectors handled per pass (at most one per lane)
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: a float add rounds to integer
 
 struct UnprojParams {
-    const uint4 *packed;   // (B*V, chunks, Hp, Wp) 16-byte texels
+    const char *packed;    // (B*V, Hp, Wp, CP) pixel-major planes
     const float *proj;     // (B, V, 3, 4)
     const float *coord;    // (B, n_extent, 3): voxels [n_origin, n_origin + n_extent)
     float *out;            // (B, C, n_extent)
     long long n0, n1;      // voxels computed by this launch
     long long n_origin, n_extent;
-    long long plane;       // Hp * Wp texels
-    int V, C, W, H, Wp, chunks;
-    int b0;
-    int gx, gy, gz;        // volume shape (gx*gy*gz == N)
-    int ltx, lty, ltz;     // log2 of the CTA brick (TX*TY*TZ == kBlock)
-    int x_lo;              // first x-plane touched by [n0,n1)
-    int tiles_y, tiles_z;
+    long long plane_bytes; // Hp * Wp * pixel bytes
+    int V, VP, C, W, H, Wp;
+    int lpb;               // log2(pixel bytes)
+    int nchunks;           // 16-byte vectors per pixel (power of two)
+    int b0, nb;
+    int gx, gy, gz;
+    int x_lo, nx;          // x planes touched by [n0,n1)
+    int lz, nseg;          // z segment length (<= kLzMax) and segments per z row
+    int warp_smem;         // bytes of shared memory per warp
+    int rec_bytes;         // bytes of one voxel record: V x float4 weights, then VP x int offsets
+    int off_tile;          // byte offset of the output tile inside a warp's smem
     float Hf, Wf, sx, sy;  // (float)H, (float)W, (W-1)/2, (H-1)/2
+    float rH, rW;          // RN(1/H), RN(1/W)
 };
 
 struct ViewCell {
-    int off;               // texel offset of the nw corner inside a padded plane
+    int off;               // pixel offset of the nw corner inside a padded plane
     float w00, w01, w10, w11;
 };
 
-// models/aggregation.py:38-51 + ATen grid_sampler unnormalize/compute_interp_params.
-__device__ __forceinline__ ViewCell make_cell(const float *Ps, float X, float Y, float Z, const UnprojParams &p)
+// a0/b, a1/b correctly rounded, sharing the reciprocal.  Same instruction
+// sequence as the div.rn.f32 fast path (MUFU.RCP, one Newton step, quotient,
+// exact remainder, correction); operands outside the safe exponent range
+// (including exact zeros) take the library division.
+__device__ __forceinline__ void div2_rn(float a0, float a1, float b, float &q0, float &q1)
 {
-    const float xw = proj_row(X, Y, Z, Ps[0], Ps[1], Ps[2], Ps[3]);
-    const float yw = proj_row(X, Y, Z, Ps[4], Ps[5], Ps[6], Ps[7]);
-    const float ww = proj_row(X, Y, Z, Ps[8], Ps[9], Ps[10], Ps[11]);
+    const float lo = fminf(fminf(fabsf(a0), fabsf(a1)), fabsf(b));
+    const float hi = fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fabsf(b));
+    if (lo > 1e-30f && hi < 1e30f) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+        const float e = __fmaf_rn(-b, r, 1.0f);
+        r = __fmaf_rn(r, e, r);
+        const float t0 = __fmul_rn(a0, r), t1 = __fmul_rn(a1, r);
+        const float m0 = __fmaf_rn(-b, t0, a0), m1 = __fmaf_rn(-b, t1, a1);
+        q0 = __fmaf_rn(r, m0, t0);
+        q1 = __fmaf_rn(r, m1, t1);
+    } else {
+        q0 = __fdiv_rn(a0, b);
+        q1 = __fdiv_rn(a1, b);
+    }
+}
+
+// x / dx and y / dy for launch constants with rd = RN(1/d): q = x*rd, r = x - d*q
+// (exact), q' = q + r*rd is the correctly rounded quotient (Markstein) for
+// operands in the safe range; checked exhaustively for the usual map sizes in
+// the tests.
+__device__ __forceinline__ void div_const2(float x, float y, float dx, float rdx, float dy, float rdy,
+                                           float &qx, float &qy)
+{
+    const float lo = fminf(fabsf(x), fabsf(y)), hi = fmaxf(fabsf(x), fabsf(y));
+    if (lo > 1e-30f && hi < 1e30f) {
+        const float a = __fmul_rn(x, rdx), c = __fmul_rn(y, rdy);
+        qx = __fmaf_rn(__fmaf_rn(-dx, a, x), rdx, a);
+        qy = __fmaf_rn(__fmaf_rn(-dy, c, y), rdy, c);
+    } else {
+        qx = __fdiv_rn(x, dx);
+        qy = __fdiv_rn(y, dy);
+    }
+}
+
+// floor of a coordinate already clamped to a small range, without the XU pipe
+__device__ __forceinline__ float floor_small(float xc, int &xi)
+{
+    const float t = __fadd_rn(xc, kMagic);
+    float r = __fsub_rn(t, kMagic);               // rint(xc)
+    xi = __float_as_int(t) - 0x4B400000;
+    if (r > xc) { r = __fsub_rn(r, 1.0f); xi -= 1; }
+    return r;
+}
+
+// models/aggregation.py:38-51 + ATen grid_sampler unnormalize/compute_interp_params
+__device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1, const float4 &P2,
+                                              float X, float Y, float Z, const UnprojParams &p)
+{
+    const float xw = proj_row(X, Y, Z, P0.x, P0.y, P0.z, P0.w);
+    const float yw = proj_row(X, Y, Z, P1.x, P1.y, P1.z, P1.w);
+    const float ww = proj_row(X, Y, Z, P2.x, P2.y, P2.z, P2.w);
     const bool invalid = ww <= 0.0f;                 // :42 depth must be > 0
     const float wd = (ww == 0.0f) ? 1.0f : ww;       // :44 not to divide by zero
-    const float x = __fdiv_rn(xw, wd);
-    const float y = __fdiv_rn(yw, wd);
+    float x, y;
+    div2_rn(xw, yw, wd, x, y);
     // :49-50  2*(x/feature_shape[0] - 0.5): x by H, y by W (reference behaviour)
-    const float gx = __fmul_rn(2.0f, __fsub_rn(__fdiv_rn(x, p.Hf), 0.5f));
-    const float gy = __fmul_rn(2.0f, __fsub_rn(__fdiv_rn(y, p.Wf), 0.5f));
+    float qx, qy;
+    div_const2(x, y, p.Hf, p.rH, p.Wf, p.rW, qx, qy);
+    const float gx = __fmul_rn(2.0f, __fsub_rn(qx, 0.5f));
+    const float gy = __fmul_rn(2.0f, __fsub_rn(qy, 0.5f));
     // align_corners=True: (g + 1) * ((size - 1) / 2)
     const float ix = __fmul_rn(__fadd_rn(gx, 1.0f), p.sx);
     const float iy = __fmul_rn(__fadd_rn(gy, 1.0f), p.sy);
-    const float xf = floorf(ix), yf = floorf(iy);
-    const float fw = __fsub_rn(ix, xf), fe = __fsub_rn(1.0f, fw);
-    const float fn = __fsub_rn(iy, yf), fs = __fsub_rn(1.0f, fn);
+    // Cell index from the position clamped into the zero border (NaN -> border).
+    // Inside the map clamped == unclamped, so floor and weights are the
+    // reference's; outside, every corner is a zero texel and only finiteness of
+    // the weights matters (0 * NaN = NaN, as in the reference).
+    const float ixc = fminf(fmaxf(ix, -2.0f), p.Wf), iyc = fminf(fmaxf(iy, -2.0f), p.Hf);
+    int x0, y0;
+    const float xf = floor_small(ixc, x0), yf = floor_small(iyc, y0);
+    float fw = __fsub_rn(ixc, xf), fn = __fsub_rn(iyc, yf);
+    if (!(fabsf(ix) < INFINITY)) fw = __int_as_float(0x7fc00000);
+    if (!(fabsf(iy) < INFINITY)) fn = __int_as_float(0x7fc00000);
+    const float fe = __fsub_rn(1.0f, fw), fs = __fsub_rn(1.0f, fn);
     ViewCell c;
     c.w00 = __fmul_rn(fs, fe); c.w01 = __fmul_rn(fs, fw);
     c.w10 = __fmul_rn(fn, fe); c.w11 = __fmul_rn(fn, fw);
-    // clamp the cell into the zero border; NaN/inf positions land in the border
-    // too and keep their NaN weights, as 0*NaN does in the reference.
-    const int x0 = (int)fminf(fmaxf(xf, -2.0f), p.Wf);
-    const int y0 = (int)fminf(fmaxf(yf, -2.0f), p.Hf);
     c.off = (y0 + kBorder) * p.Wp + (x0 + kBorder);
     if (invalid) {                                   // :62 zero out non-valid points
         c.off = 0;                                   // four border texels: exact +0
@@ -86,230 +169,433 @@ __device__ __forceinline__ ViewCell make_cell(const float *Ps, float X, float Y,
     return c;
 }
 
-__device__ __forceinline__ float blend(float t00, float t01, float t10, float t11, const ViewCell &c)
+// ---- packed f32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) ---------------
+typedef unsigned long long u64;
+struct f2 { float x, y; };
+__device__ __forceinline__ u64 pk(float a, float b)
 {
-    float acc = __fmul_rn(t00, c.w00);
-    acc = __fmaf_rn(t01, c.w01, acc);
-    acc = __fmaf_rn(t10, c.w10, acc);
-    return __fmaf_rn(t11, c.w11, acc);
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
 }
-
-__device__ __forceinline__ float bf_lo(unsigned u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(unsigned u) { return __uint_as_float(u & 0xffff0000u); }
-
-// 8 channels of one view: s[0..7]
-template <bool BF16>
-__device__ __forceinline__ void sample8(float *s, const uint4 *base, long long plane, int Wp, const ViewCell &c)
+__device__ __forceinline__ f2 upk(u64 v)
 {
-    if (BF16) {
-        const uint4 a = __ldg(base), b = __ldg(base + 1), d = __ldg(base + Wp), e = __ldg(base + Wp + 1);
-        s[0] = blend(bf_lo(a.x), bf_lo(b.x), bf_lo(d.x), bf_lo(e.x), c);
-        s[1] = blend(bf_hi(a.x), bf_hi(b.x), bf_hi(d.x), bf_hi(e.x), c);
-        s[2] = blend(bf_lo(a.y), bf_lo(b.y), bf_lo(d.y), bf_lo(e.y), c);
-        s[3] = blend(bf_hi(a.y), bf_hi(b.y), bf_hi(d.y), bf_hi(e.y), c);
-        s[4] = blend(bf_lo(a.z), bf_lo(b.z), bf_lo(d.z), bf_lo(e.z), c);
-        s[5] = blend(bf_hi(a.z), bf_hi(b.z), bf_hi(d.z), bf_hi(e.z), c);
-        s[6] = blend(bf_lo(a.w), bf_lo(b.w), bf_lo(d.w), bf_lo(e.w), c);
-        s[7] = blend(bf_hi(a.w), bf_hi(b.w), bf_hi(d.w), bf_hi(e.w), c);
-    } else {
-        const float4 *f = reinterpret_cast<const float4 *>(base);
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const float4 *q = f + k * plane;
-            const float4 a = __ldg(q), b = __ldg(q + 1), d = __ldg(q + Wp), e = __ldg(q + Wp + 1);
-            s[4 * k + 0] = blend(a.x, b.x, d.x, e.x, c);
-            s[4 * k + 1] = blend(a.y, b.y, d.y, e.y, c);
-            s[4 * k + 2] = blend(a.z, b.z, d.z, e.z, c);
-            s[4 * k + 3] = blend(a.w, b.w, d.w, e.w, c);
-        }
-    }
+    f2 r;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
 }
-
-// bare MUFU.EX2: arguments here are always <= 0, results in [0,1]; 2^-22 relative
-__device__ __forceinline__ float ex2_approx(float x)
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 mul2(u64 a, u64 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float ex2_approx(float x)   // bare MUFU.EX2; arguments here are <= 0
 {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float max_nan(float a, float b)
 {
     float r;
     asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));   // torch.max propagates NaN
     return r;
 }
+__device__ __forceinline__ float bf_lo(unsigned u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf_hi(unsigned u) { return __uint_as_float(u & 0xffff0000u); }
 
-// Running fusion state of one channel across views (views arrive in order).
+// Blend of one channel pair: mul, then three FMAs (== ATen's contraction order)
+__device__ __forceinline__ u64 blend2(u64 t00, u64 t01, u64 t10, u64 t11, u64 w00, u64 w01, u64 w10, u64 w11)
+{
+    u64 acc = mul2(t00, w00);
+    acc = fma2(t01, w01, acc);
+    acc = fma2(t10, w10, acc);
+    return fma2(t11, w11, acc);
+}
+
+// NP channel pairs of one view from its four corner texels
+template <bool BF16>
+__device__ __forceinline__ void blend_texels(u64 *s, const uint4 &a, const uint4 &b, const uint4 &d,
+                                             const uint4 &e, const float4 &w)
+{
+    const u64 w00 = pk(w.x, w.x), w01 = pk(w.y, w.y), w10 = pk(w.z, w.z), w11 = pk(w.w, w.w);
+    if (BF16) {
+        const unsigned ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
+        const unsigned ud[4] = {d.x, d.y, d.z, d.w}, ue[4] = {e.x, e.y, e.z, e.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            s[i] = blend2(pk(bf_lo(ua[i]), bf_hi(ua[i])), pk(bf_lo(ub[i]), bf_hi(ub[i])),
+                          pk(bf_lo(ud[i]), bf_hi(ud[i])), pk(bf_lo(ue[i]), bf_hi(ue[i])), w00, w01, w10, w11);
+    } else {
+        s[0] = blend2(pk(__uint_as_float(a.x), __uint_as_float(a.y)), pk(__uint_as_float(b.x), __uint_as_float(b.y)),
+                      pk(__uint_as_float(d.x), __uint_as_float(d.y)), pk(__uint_as_float(e.x), __uint_as_float(e.y)),
+                      w00, w01, w10, w11);
+        s[1] = blend2(pk(__uint_as_float(a.z), __uint_as_float(a.w)), pk(__uint_as_float(b.z), __uint_as_float(b.w)),
+                      pk(__uint_as_float(d.z), __uint_as_float(d.w)), pk(__uint_as_float(e.z), __uint_as_float(e.w)),
+                      w00, w01, w10, w11);
+    }
+}
+
+// View fusion of one channel pair; views arrive in order, VMAX at a time.
 //   sum/mean: acc = ((s0 + s1) + s2) ...   (the reference's order)
-//   max     : running max
+//   max     : running max (NaN propagating, like torch.max)
 //   softmax : (m, S = sum e^(s-m), A = sum s*e^(s-m)); result A / S
-template <int METHOD>
-struct Fuse {
-    float a, m, S;
-    __device__ __forceinline__ void init() { a = 0.0f; m = -INFINITY; S = 0.0f; }
-    // one block of nv views; `first` = no state yet
-    template <int VMAX>
-    __device__ __forceinline__ void absorb(const float (*s)[kGroupCh], int ch, int nv, bool first)
+template <int METHOD, int VMAX, bool EXACT>
+struct Fuse2 {
+    u64 a, S;
+    float m0, m1;
+    __device__ __forceinline__ void absorb(const u64 *s, int stride, int nv, bool first)
     {
         if (METHOD == MVHMR_SUM || METHOD == MVHMR_MEAN) {
-            float acc = first ? s[0][ch] : __fadd_rn(a, s[0][ch]);
+            u64 acc = first ? s[0] : add2(a, s[0]);
 #pragma unroll
-            for (int v = 1; v < VMAX; ++v) if (v < nv) acc = __fadd_rn(acc, s[v][ch]);
+            for (int v = 1; v < VMAX; ++v) if (EXACT || v < nv) acc = add2(acc, s[v * stride]);
             a = acc;
         } else if (METHOD == MVHMR_MAX) {
-            float mm = first ? s[0][ch] : max_nan(m, s[0][ch]);
+            f2 x = upk(s[0]);
+            float a0 = first ? x.x : max_nan(m0, x.x), a1 = first ? x.y : max_nan(m1, x.y);
 #pragma unroll
-            for (int v = 1; v < VMAX; ++v) if (v < nv) mm = max_nan(mm, s[v][ch]);
-            m = mm;
+            for (int v = 1; v < VMAX; ++v) if (EXACT || v < nv) {
+                x = upk(s[v * stride]);
+                a0 = max_nan(a0, x.x); a1 = max_nan(a1, x.y);
+            }
+            m0 = a0; m1 = a1;
         } else {
-            float mb = s[0][ch];
+            f2 x = upk(s[0]);
+            float b0 = x.x, b1 = x.y;
 #pragma unroll
-            for (int v = 1; v < VMAX; ++v) if (v < nv) mb = fmaxf(mb, s[v][ch]);
-            float SS = 0.0f, AA = 0.0f;
+            for (int v = 1; v < VMAX; ++v) if (EXACT || v < nv) {
+                x = upk(s[v * stride]);
+                b0 = fmaxf(b0, x.x); b1 = fmaxf(b1, x.y);
+            }
+            u64 SS = pk(0.0f, 0.0f), AA = SS;
             if (!first) {
-                const float mn = fmaxf(m, mb);
-                const float sc = ex2_approx(__fsub_rn(m, mn) * kLog2e);
-                SS = S * sc; AA = a * sc; mb = mn;
+                const float n0 = fmaxf(m0, b0), n1 = fmaxf(m1, b1);
+                const u64 sc = pk(ex2_approx((m0 - n0) * kLog2e), ex2_approx((m1 - n1) * kLog2e));
+                SS = mul2(S, sc); AA = mul2(a, sc);
+                b0 = n0; b1 = n1;
             }
+            // exp(s - m) = 2^(s*log2e - m*log2e): one packed FMA for two arguments.  The
+            // rounding of m*log2e is common to all views and cancels in A / S.
+            const u64 L2 = pk(kLog2e, kLog2e), nm = pk(-b0 * kLog2e, -b1 * kLog2e);
 #pragma unroll
-            for (int v = 0; v < VMAX; ++v) if (v < nv) {
-                const float e = ex2_approx(__fsub_rn(s[v][ch], mb) * kLog2e);
-                SS += e;
-                AA = fmaf(s[v][ch], e, AA);
+            for (int v = 0; v < VMAX; ++v) if (EXACT || v < nv) {
+                const f2 arg = upk(fma2(s[v * stride], L2, nm));
+                const u64 e = pk(ex2_approx(arg.x), ex2_approx(arg.y));
+                SS = add2(SS, e);
+                AA = fma2(s[v * stride], e, AA);
             }
-            m = mb; S = SS; a = AA;
+            m0 = b0; m1 = b1; S = SS; a = AA;
         }
     }
-    __device__ __forceinline__ float result(float Vf) const
+    __device__ __forceinline__ f2 result(float Vf) const
     {
-        if (METHOD == MVHMR_SUM) return a;
-        if (METHOD == MVHMR_MEAN) return __fdiv_rn(a, Vf);
-        if (METHOD == MVHMR_MAX) return m;
-        return __fdividef(a, S);
+        if (METHOD == MVHMR_SUM) return upk(a);
+        if (METHOD == MVHMR_MEAN) { f2 r = upk(a); r.x = __fdiv_rn(r.x, Vf); r.y = __fdiv_rn(r.y, Vf); return r; }
+        if (METHOD == MVHMR_MAX) { f2 r; r.x = m0; r.y = m1; return r; }
+        const f2 s = upk(S);
+        return upk(mul2(a, pk(rcp_approx(s.x), rcp_approx(s.y))));
     }
 };
 
-template <int VMAX, bool BF16, int METHOD, bool MULTI>
-__global__ void __launch_bounds__(kBlock)
+// VMAX : views held in registers at once (V > VMAX walks view blocks, fusion state carried)
+// EXACT: V == VMAX — view loops are straight-line code, record layout is a compile-time constant
+// CACHE: keep the corner texels of every view across the z walk
+// LPB  : log2(pixel bytes) as a compile-time constant (0 = take it from the parameters), so that
+//        the second texel of a row is an immediate offset and offsets shift by an immediate
+//
+// Grid: x = blocks of kWarps consecutive x planes, y = voxel row y, z = sample * nseg + z segment.
+// One warp = one task = one z segment (<= 32 voxels) of one (sample, x, y) row; the warps of a
+// CTA take consecutive x planes, whose projections overlap almost completely in every view, so
+// the CTA's texel footprint stays L1-resident.
+template <int VMAX, bool EXACT, bool CACHE, bool BF16, int METHOD, int LPB>
+__global__ void __launch_bounds__(kWarps * 32, MVHMR_MINBLOCKS)
 unproject_kernel(const UnprojParams p)
 {
-    extern __shared__ float Psm[];                   // V x 12 projection entries of sample b
-    const int b = p.b0 + blockIdx.y;
-    for (int i = threadIdx.x; i < p.V * 12; i += kBlock) Psm[i] = __ldg(p.proj + (size_t)b * p.V * 12 + i);
-    __syncthreads();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NP = BF16 ? 4 : 2;                 // channel pairs per lane per pass
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int xi = blockIdx.x * kWarps + warp;
+    if (xi >= p.nx) return;                          // warps are independent: no block-level barrier anywhere
+    const int vx = p.x_lo + xi;
+    const int vy = blockIdx.y;
+    const int seg = blockIdx.z % (unsigned)p.nseg;
+    const int b = p.b0 + blockIdx.z / (unsigned)p.nseg;
 
-    // brick coordinates: z fastest inside the warp, then x, then y
-    const int t = threadIdx.x;
-    const int lz = t & ((1 << p.ltz) - 1);
-    const int lx = (t >> p.ltz) & ((1 << p.ltx) - 1);
-    const int ly = t >> (p.ltz + p.ltx);
-    int tile = blockIdx.x;
-    const int tz = tile % p.tiles_z; tile /= p.tiles_z;
-    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
-    const int vx = p.x_lo + (tile << p.ltx) + lx;
-    const int vy = (ty << p.lty) + ly;
-    const int vz = (tz << p.ltz) + lz;
-    if (vx >= p.gx || vy >= p.gy || vz >= p.gz) return;
-    const long long n = ((long long)vx * p.gy + vy) * p.gz + vz;
-    if (n < p.n0 || n >= p.n1) return;
+    unsigned char *recs = smem_raw + (size_t)warp * p.warp_smem;
+    // per-voxel records: V x float4 bilinear weights, then VP x int pixel offsets (-1: voxel not
+    // in the shard window).  Records of different lane groups are skewed by 16 bytes so that
+    // the groups' broadcast reads fall into different banks.
+    float4 *tile = reinterpret_cast<float4 *>(recs + p.off_tile);    // [lz][nvec] output staging
 
-    const long long nl = n - p.n_origin;
-    const float *xyz = p.coord + ((size_t)b * p.n_extent + nl) * 3;
-    const float X = __ldg(xyz), Y = __ldg(xyz + 1), Z = __ldg(xyz + 2);
-
-    ViewCell cell[VMAX];
-    if (!MULTI) {
-#pragma unroll
-        for (int v = 0; v < VMAX; ++v) if (v < p.V) cell[v] = make_cell(Psm + 12 * v, X, Y, Z, p);
-    }
-
-    const int stride_k = BF16 ? 1 : 2;               // texel chunks per 8 channels
+    const int lpb = LPB ? LPB : p.lpb;
+    const int nch_pass = LPB ? ((1 << LPB) / 16 < kVecPass ? (1 << LPB) / 16 : kVecPass) : min(p.nchunks, kVecPass);
+    const int lpv_log = 31 - __clz(nch_pass);
+    const int ngroups = 32 >> lpv_log;               // voxels served per warp step
+    const int grp = lane >> lpv_log, chunk = lane & (nch_pass - 1);
+    const int nvec = BF16 ? 2 * nch_pass : nch_pass; // float4 vectors per tile row
     const float Vf = (float)p.V;
-    float *outp = p.out + (size_t)b * p.C * p.n_extent + nl;
-    const uint4 *fb = p.packed + (size_t)b * p.V * p.chunks * p.plane;
+    const unsigned px = 1u << lpb, row = (unsigned)p.Wp << lpb;
+    const int wbytes = EXACT ? VMAX * 16 : p.V * 16;
+    const int rec_bytes = EXACT ? VMAX * 16 + ((VMAX + 3) & ~3) * 4 : p.rec_bytes;
 
-    for (int c0 = 0; c0 < p.C; c0 += kGroupCh) {
-        const int k0 = (c0 / kGroupCh) * stride_k;
-        Fuse<METHOD> fz[kGroupCh];
-        for (int vb = 0; vb < p.V; vb += VMAX) {
-            const int nv = min(VMAX, p.V - vb);
-            if (MULTI) {
+    const int z0 = seg * p.lz;
+    const int zn = min(p.lz, p.gz - z0);             // voxels in this segment (<= 32)
+    const int steps = (zn + ngroups - 1) >> (5 - lpv_log);
+    const long long nrow = ((long long)vx * p.gy + vy) * p.gz + z0;   // flattened index of the first voxel
+    const long long nme = nrow + lane;               // the voxel this lane projects / writes
+    const bool mine = (lane < zn) && (nme >= p.n0) && (nme < p.n1);
+
+    // ---- phase A: one voxel per lane, projected through every view ----
+    if (lane < zn) {
+        const float *xyz = p.coord + ((size_t)b * p.n_extent + (mine ? nme - p.n_origin : 0)) * 3;
+        const float X = mine ? __ldg(xyz) : 0.0f, Y = mine ? __ldg(xyz + 1) : 0.0f, Z = mine ? __ldg(xyz + 2) : 0.0f;
+        unsigned char *rec = recs + lane * rec_bytes + (lane / steps) * 16;
+        const float4 *Pb = reinterpret_cast<const float4 *>(p.proj + (size_t)b * p.V * 12);
+        for (int v = 0; v < p.V; ++v) {
+            const float4 P0 = __ldg(Pb + 3 * v), P1 = __ldg(Pb + 3 * v + 1), P2 = __ldg(Pb + 3 * v + 2);
+            const ViewCell c = make_cell(P0, P1, P2, X, Y, Z, p);
+            reinterpret_cast<float4 *>(rec)[v] = make_float4(c.w00, c.w01, c.w10, c.w11);
+            reinterpret_cast<int *>(rec + wbytes)[v] = mine ? c.off : -1;
+        }
+    }
+    __syncwarp();
+
+    const bool single = EXACT || p.V <= VMAX;        // all views fit one register block
+    for (int cb = 0; cb < p.nchunks; cb += kVecPass) {           // channel passes (C > 128 fp32 / 256 bf16)
+        const char *lane_base = p.packed + (size_t)b * p.V * p.plane_bytes + ((size_t)(cb + chunk) << 4);
+        const char *vbase[VMAX];
 #pragma unroll
-                for (int v = 0; v < VMAX; ++v) if (v < nv) cell[v] = make_cell(Psm + 12 * (vb + v), X, Y, Z, p);
-            }
-            float s[VMAX][kGroupCh];
+        for (int v = 0; v < VMAX; ++v) vbase[v] = lane_base + (size_t)v * p.plane_bytes;
+        constexpr int TV = VMAX < 4 ? VMAX : 4;      // views whose texels are in registers at once
+        uint4 tex[TV][4];
+        int cur[TV];
 #pragma unroll
-            for (int v = 0; v < VMAX; ++v) if (v < nv) {
-                const uint4 *base = fb + ((size_t)(vb + v) * p.chunks + k0) * p.plane + cell[v].off;
-                if (!BF16 && k0 + 1 >= p.chunks) {   // C % 8 in (0,4]: second chunk absent
-                    float4 const *q = reinterpret_cast<const float4 *>(base);
-                    const float4 a = __ldg(q), bb = __ldg(q + 1), d = __ldg(q + p.Wp), e = __ldg(q + p.Wp + 1);
-                    s[v][0] = blend(a.x, bb.x, d.x, e.x, cell[v]); s[v][1] = blend(a.y, bb.y, d.y, e.y, cell[v]);
-                    s[v][2] = blend(a.z, bb.z, d.z, e.z, cell[v]); s[v][3] = blend(a.w, bb.w, d.w, e.w, cell[v]);
-                    s[v][4] = s[v][5] = s[v][6] = s[v][7] = 0.0f;
-                } else {
-                    sample8<BF16>(s[v], base, p.plane, p.Wp, cell[v]);
+        for (int v = 0; v < TV; ++v) cur[v] = -2;
+
+        // gathers of up to TV views [v0, v0+nv) for the voxel whose record is r; returns false if
+        // the voxel is outside the shard window
+        auto gather = [&](const unsigned char *r, int v0, int nv) -> bool {
+            const int4 o4 = *reinterpret_cast<const int4 *>(r + wbytes + v0 * 4);
+            const int off[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+            for (int v = 0; v < TV; ++v) {
+                if (EXACT || v < nv) {
+                    const int o = max(off[v], 0);
+                    if (!CACHE || o != cur[v]) {
+                        const char *q0 = (single && VMAX <= 4 ? vbase[v % VMAX] : lane_base + (size_t)(v0 + v) * p.plane_bytes)
+                                         + ((unsigned)o << lpb);
+                        const char *q1 = q0 + row;
+                        tex[v][0] = __ldg(reinterpret_cast<const uint4 *>(q0));
+                        tex[v][1] = __ldg(reinterpret_cast<const uint4 *>(q0 + px));
+                        tex[v][2] = __ldg(reinterpret_cast<const uint4 *>(q1));
+                        tex[v][3] = __ldg(reinterpret_cast<const uint4 *>(q1 + px));
+                        cur[v] = o;
+                    }
                 }
             }
-#pragma unroll
-            for (int ch = 0; ch < kGroupCh; ++ch) fz[ch].template absorb<VMAX>(s, ch, nv, vb == 0);
-            if (!MULTI) break;
-        }
-#pragma unroll
-        for (int ch = 0; ch < kGroupCh; ++ch)
-            if (c0 + ch < p.C) __stcs(outp + (size_t)(c0 + ch) * p.n_extent, fz[ch].result(Vf));
-    }
-}
+            return off[0] >= 0;
+        };
 
-// NCHW -> padded 16-byte-texel planes.  One thread per padded texel.
-template <bool BF16>
-__global__ void __launch_bounds__(256)
-pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, size_t total,
-            int C, int H, int W, int chunks, int Hp, int Wp)
-{
-    constexpr int CPT = BF16 ? 8 : 4;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % Wp) - kBorder;
-        size_t r = idx / Wp;
-        const int y = (int)(r % Hp) - kBorder; r /= Hp;
-        const int k = (int)(r % chunks);
-        const size_t bv = r / chunks;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-        if (x >= 0 && x < W && y >= 0 && y < H) {
-            const size_t pix = (size_t)y * W + x, hw = (size_t)H * W;
-            if (BF16) {
-                const unsigned short *src = static_cast<const unsigned short *>(feats) + (bv * C + (size_t)k * CPT) * hw + pix;
-                unsigned h[8];
+        // ---- phase B: each lane group walks its run of consecutive z voxels ----
+        const unsigned char *rec = recs + (grp * steps) * rec_bytes + grp * 16;
+        int zl = grp * steps;
+        bool store_next = false;
+        const bool piped = single && CACHE && VMAX <= 4;   // the cached path software-pipelines its gathers
+        if (piped) store_next = gather(zl < zn ? rec : recs, 0, p.V) && (zl < zn);
+        for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
+            const unsigned char *r = zl < zn ? rec : recs;
+            Fuse2<METHOD, VMAX, EXACT> fz[NP];
+            bool store = store_next;
+            if (piped) {
+                // software pipeline: blend this voxel, issue the next voxel's gathers, then do the
+                // view fusion (exp, sums) while those loads are in flight
+                u64 s[VMAX][NP];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) h[i] = (k * CPT + i < C) ? (unsigned)__ldg(src + i * hw) : 0u;
-                v = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                for (int v = 0; v < TV; ++v)
+                    if (EXACT || v < p.V)
+                        blend_texels<BF16>(s[v], tex[v][0], tex[v][1], tex[v][2], tex[v][3],
+                                           reinterpret_cast<const float4 *>(r)[v]);
+                if (st + 1 < steps) store_next = gather(zl + 1 < zn ? rec + rec_bytes : recs, 0, p.V) && (zl + 1 < zn);
+#pragma unroll
+                for (int i = 0; i < NP; ++i) fz[i].absorb(&s[0][i], NP, p.V, true);
             } else {
-                const float *src = static_cast<const float *>(feats) + (bv * C + (size_t)k * CPT) * hw + pix;
-                float f[4];
+                store = zl < zn;
+                for (int vb = 0; vb < p.V; vb += VMAX) {
+                    const int nv = EXACT ? VMAX : min(VMAX, p.V - vb);
+                    u64 s[VMAX][NP];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) f[i] = (k * CPT + i < C) ? __ldg(src + i * hw) : 0.0f;
-                v = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+                    for (int v4 = 0; v4 < VMAX; v4 += TV) {      // TV views at a time
+                        if (EXACT || v4 < nv) {
+                            const int n4 = EXACT ? TV : min(TV, nv - v4);
+                            const bool inwin = gather(r, vb + v4, n4);
+                            if (v4 == 0 && vb == 0) store = store && inwin;
+#pragma unroll
+                            for (int v = 0; v < TV; ++v)
+                                if (EXACT || v < n4)
+                                    blend_texels<BF16>(s[v4 + v], tex[v][0], tex[v][1], tex[v][2], tex[v][3],
+                                                       reinterpret_cast<const float4 *>(r)[vb + v4 + v]);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) fz[i].absorb(&s[0][i], NP, nv, vb == 0);
+                }
+            }
+            if (store) {                                     // row zl of the tile, vector position swizzled by z
+#pragma unroll
+                for (int h = 0; h < NP / 2; ++h) {
+                    const f2 r0 = fz[2 * h].result(Vf), r1 = fz[2 * h + 1].result(Vf);
+                    const int vec = BF16 ? 2 * chunk + h : chunk;
+                    tile[zl * nvec + (vec ^ (zl & (nvec - 1)))] = make_float4(r0.x, r0.y, r1.x, r1.y);
+                }
             }
         }
-        packed[idx] = v;
+        __syncwarp();
+        // ---- read out: lane <-> voxel, one coalesced 128-byte store per channel ----
+        {
+            const int c_base = (BF16 ? 8 : 4) * cb;
+            const int zr = mine ? lane : 0;
+            float *o = p.out + ((size_t)b * p.C + c_base) * p.n_extent + (mine ? nme - p.n_origin : 0);
+            const float4 *trow = tile + zr * nvec;
+            const int sw = zr & (nvec - 1);
+            const int kfull = min(nvec, (p.C - c_base) >> 2);        // vectors with all four channels present
+            const size_t cs = (size_t)p.n_extent;
+            int k = 0;
+            for (; k < kfull; ++k, o += 4 * cs) {
+                const float4 rr = trow[k ^ sw];
+                if (mine) { __stcs(o, rr.x); __stcs(o + cs, rr.y); __stcs(o + 2 * cs, rr.z); __stcs(o + 3 * cs, rr.w); }
+            }
+            if (k < nvec && c_base + 4 * k < p.C) {                  // ragged last vector (C % 4 != 0)
+                const float4 rr = trow[k ^ sw];
+                const int c = c_base + 4 * k;
+                if (mine) {
+                    __stcs(o, rr.x);
+                    if (c + 1 < p.C) __stcs(o + cs, rr.y);
+                    if (c + 2 < p.C) __stcs(o + 2 * cs, rr.z);
+                }
+            }
+        }
+        __syncwarp();
     }
 }
 
+// NCHW -> pixel-major padded planes.  One CTA per padded row: channel planes are
+// read with coalesced runs along x into a shared tile, pixels are written as whole
+// contiguous channel vectors (the full row is one contiguous run in the packed
+// layout).  Border rows / columns are written as zeros.  No divisions per element.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, int H, int W,
+            int nchunks, int Hp, int Wp)
+{
+    constexpr int CPT = BF16 ? 8 : 4;            // channels per 16-byte vector
+    constexpr int CB = 64;                       // channels per tile
+    constexpr int XB = 128;                      // pixels per tile
+    __shared__ float tile_f[BF16 ? 1 : CB * (XB + 1)];
+    __shared__ unsigned short tile_h[BF16 ? CB * (XB + 2) : 1];
+    const int bv = blockIdx.x / Hp;
+    const int y = blockIdx.x % Hp - kBorder;
+    uint4 *dst_row = packed + (size_t)blockIdx.x * Wp * nchunks;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (y < 0 || y >= H) {
+        for (int e = threadIdx.x; e < Wp * nchunks; e += blockDim.x) dst_row[e] = make_uint4(0u, 0u, 0u, 0u);
+        return;
+    }
+    const int CP = nchunks * CPT;
+    const int kn_all = (CB / CPT < nchunks) ? CB / CPT : nchunks;      // vectors per channel block (power of two)
+    const int kshift = 31 - __clz(kn_all);
+    for (int x0 = -kBorder; x0 < W + kBorder; x0 += XB) {
+        const int xn = min(XB, W + kBorder - x0);                      // padded pixels in this block
+        for (int cb = 0; cb < CP; cb += CB) {
+            const int cn = min(CB, CP - cb);
+            for (int c = warp; c < cn; c += 8) {
+                const size_t src_row = ((size_t)(bv * C + cb + c) * H + y) * W;
+                for (int j = lane; j < xn; j += 32) {
+                    const int x = x0 + j;
+                    const bool in = (cb + c < C) && x >= 0 && x < W;
+                    if (BF16) tile_h[c * (XB + 2) + j] = in ? __ldg(static_cast<const unsigned short *>(feats) + src_row + x) : (unsigned short)0;
+                    else tile_f[c * (XB + 1) + j] = in ? __ldg(static_cast<const float *>(feats) + src_row + x) : 0.0f;
+                }
+            }
+            __syncthreads();
+            const int kn = cn / CPT;
+            for (int e = threadIdx.x; e < (xn << kshift); e += blockDim.x) {
+                const int j = e >> kshift, k = e & (kn_all - 1);
+                if (k < kn) {
+                    uint4 v;
+                    if (BF16) {
+                        unsigned h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) h[i] = tile_h[(k * 8 + i) * (XB + 2) + j];
+                        v = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                    } else {
+                        v = make_uint4(__float_as_uint(tile_f[(k * 4 + 0) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 1) * (XB + 1) + j]),
+                                       __float_as_uint(tile_f[(k * 4 + 2) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 3) * (XB + 1) + j]));
+                    }
+                    dst_row[(size_t)(x0 + kBorder + j) * nchunks + cb / CPT + k] = v;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+static int pow2ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; }
 
-static int chunks_of(int dtype, int C) { return dtype == MVHMR_BF16 ? (C + 7) / 8 : (C + 3) / 4; }
+// 16-byte channel vectors per pixel, padded to a power of two
+static int nchunks_of(int dtype, int C) { return pow2ceil(dtype == MVHMR_BF16 ? (C + 7) / 8 : (C + 3) / 4); }
 
-template <int VMAX, bool BF16, bool MULTI>
-static void launch_method(int method, dim3 grid, size_t smem, cudaStream_t st, const UnprojParams &p)
+template <int VMAX, bool EXACT, bool CACHE, bool BF16, int LPB>
+static cudaError_t launch_method(int method, dim3 grid, size_t smem, cudaStream_t st, const UnprojParams &p)
 {
-    switch (method) {
-    case MVHMR_SUM: unproject_kernel<VMAX, BF16, MVHMR_SUM, MULTI><<<grid, kBlock, smem, st>>>(p); break;
-    case MVHMR_MEAN: unproject_kernel<VMAX, BF16, MVHMR_MEAN, MULTI><<<grid, kBlock, smem, st>>>(p); break;
-    case MVHMR_MAX: unproject_kernel<VMAX, BF16, MVHMR_MAX, MULTI><<<grid, kBlock, smem, st>>>(p); break;
-    default: unproject_kernel<VMAX, BF16, MVHMR_SOFTMAX, MULTI><<<grid, kBlock, smem, st>>>(p); break;
+#define MVHMR_LAUNCH(M)                                                                                         \
+    {                                                                                                           \
+        auto kern = unproject_kernel<VMAX, EXACT, CACHE, BF16, M, LPB>;                                         \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+        if (e != cudaSuccess) return e;                                                                         \
+        kern<<<grid, kWarps * 32, smem, st>>>(p);                                                               \
     }
+    switch (method) {
+    case MVHMR_SUM: MVHMR_LAUNCH(MVHMR_SUM) break;
+    case MVHMR_MEAN: MVHMR_LAUNCH(MVHMR_MEAN) break;
+    case MVHMR_MAX: MVHMR_LAUNCH(MVHMR_MAX) break;
+    default: MVHMR_LAUNCH(MVHMR_SOFTMAX) break;
+    }
+#undef MVHMR_LAUNCH
+    return cudaSuccess;
+}
+
+// EXACT view counts get the pixel size as a compile-time constant for the common layouts
+// (64 / 128 / 256 bytes per pixel: 32 bf16, 32 fp32 or 64 bf16, 64 fp32 channels).
+template <int VMAX, bool EXACT, bool CACHE, bool BF16>
+static cudaError_t launch_lpb(int method, dim3 grid, size_t smem, cudaStream_t st, const UnprojParams &p)
+{
+    if (EXACT) {
+        if (p.lpb == 6) return launch_method<VMAX, EXACT, CACHE, BF16, EXACT ? 6 : 0>(method, grid, smem, st, p);
+        if (p.lpb == 7) return launch_method<VMAX, EXACT, CACHE, BF16, EXACT ? 7 : 0>(method, grid, smem, st, p);
+        if (p.lpb == 8) return launch_method<VMAX, EXACT, CACHE, BF16, EXACT ? 8 : 0>(method, grid, smem, st, p);
+    }
+    return launch_method<VMAX, EXACT, CACHE, BF16, 0>(method, grid, smem, st, p);
 }
 
 }  // namespace mvhmr
@@ -319,7 +605,7 @@ using namespace mvhmr;
 extern "C" size_t mvhmr_packed_bytes(int feat_dtype, int BV, int C, int H, int W)
 {
     if ((feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16) || BV < 0 || C < 1 || H < 1 || W < 1) return 0;
-    return (size_t)BV * chunks_of(feat_dtype, C) * (H + 2 * kBorder) * (W + 2 * kBorder) * sizeof(uint4);
+    return (size_t)BV * nchunks_of(feat_dtype, C) * (H + 2 * kBorder) * (W + 2 * kBorder) * sizeof(uint4);
 }
 
 extern "C" size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, int V, int C, int H, int W)
@@ -339,15 +625,13 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     if (BV == 0) return MVHMR_OK;
     if (!feats || !packed) return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: null pointer");
     if ((uintptr_t)packed & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: packed buffer must be 16-byte aligned");
-    const int chunks = chunks_of(feat_dtype, C), Hp = H + 2 * kBorder, Wp = W + 2 * kBorder;
-    const size_t total = (size_t)BV * chunks * Hp * Wp;
-    size_t g = (total + 255) / 256;
-    const size_t cap = 148u * 32u;
-    const unsigned grid = (unsigned)(g > cap ? cap : g);
+    const int nchunks = nchunks_of(feat_dtype, C), Hp = H + 2 * kBorder, Wp = W + 2 * kBorder;
+    const long long rows = (long long)BV * Hp;
+    if (rows > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: too many rows");
     if (feat_dtype == MVHMR_BF16)
-        pack_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(feats, (uint4 *)packed, total, C, H, W, chunks, Hp, Wp);
+        pack_kernel<true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
     else
-        pack_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(feats, (uint4 *)packed, total, C, H, W, chunks, Hp, Wp);
+        pack_kernel<false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
     return check_launch("pack_kernel");
 }
 
@@ -376,77 +660,92 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
     if (n_origin < 0 || n_extent < 0 || n0 < n_origin || n1 > n_origin + n_extent)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: voxels [%lld,%lld) not inside the buffers' range [%lld,%lld)",
                     n0, n1, n_origin, n_origin + n_extent);
+    if (tile_hint > (unsigned)kLzMax)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: tile_hint %u (z-segment length) must be <= %d", tile_hint, kLzMax);
     if (b0 == b1 || n0 == n1) return MVHMR_OK;
-    if (b1 - b0 > 65535) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: more than 65535 samples per call");
     if (!feats || !proj || !coord || !out) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
-    if ((long long)H * W > (1LL << 30)) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: feature map too large");
-
-    // CTA brick: z fastest.  Default: the largest power-of-two z run <= 32 that
-    // divides gz (full 128-byte store lines when gz % 32 == 0), the rest of the
-    // 256 threads along x, so that one CTA covers an x-z slab at fixed y.
-    int TX, TY, TZ;
-    if (tile_hint) {
-        TX = tile_hint & 0xff; TY = (tile_hint >> 8) & 0xff; TZ = (tile_hint >> 16) & 0xff;
-        if (ilog2_exact(TX) < 0 || ilog2_exact(TY) < 0 || ilog2_exact(TZ) < 0 || TX * TY * TZ != kBlock)
-            return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: tile_hint %ux%ux%u must be powers of two with product %d",
-                        TX, TY, TZ, kBlock);
-    } else {
-        TZ = 32;
-        if (gz < 32) { TZ = 1; while (TZ < gz) TZ <<= 1; }
-        else if (gz % 32 != 0) { if (gz % 16 == 0) TZ = 16; else if (gz % 8 == 0) TZ = 8; }
-        const int rest = kBlock / TZ;
-        TX = 1; while (TX < rest && TX < gx) TX <<= 1;
-        TY = rest / TX;
-    }
+    if ((long long)(H + 4) * (W + 4) * nchunks_of(feat_dtype, C) * 16 >= (1LL << 31))
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: one padded feature map must stay below 2 GiB");
+    if ((uintptr_t)proj & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: proj must be 16-byte aligned");
 
     cudaStream_t st = (cudaStream_t)stream;
-    const int chunks = chunks_of(feat_dtype, C);
-    const uint4 *packed;
+    const int nchunks = nchunks_of(feat_dtype, C);
+    const bool bf = feat_dtype == MVHMR_BF16;
+
+    // z-segment length of a warp task and the per-warp shared-memory layout
+    const int nch_pass = nchunks < kVecPass ? nchunks : kVecPass;
+    const int nvec = bf ? 2 * nch_pass : nch_pass;
+    const int VP = (V <= 4) ? 4 : ((V + 7) & ~7);
+    int lz_cap = 256 / nvec;                                       // output tile <= 4 KB per warp
+    if (lz_cap < 4) lz_cap = 4;
+    if (lz_cap > MVHMR_LZCAP) lz_cap = MVHMR_LZCAP;
+    const int rec_bytes = V * 16 + VP * 4;
+    while (lz_cap > 1 && (size_t)lz_cap * rec_bytes > 12 * 1024) lz_cap >>= 1;             // voxel records <= 12 KB per warp
+    int lz = (int)tile_hint;
+    if (lz == 0) {
+        const int parts = (gz + lz_cap - 1) / lz_cap;               // smallest equal split of a z row
+        lz = (gz + parts - 1) / parts;
+    }
+    int off_tile, warp_smem;
+    size_t smem;
+    for (;;) {                                                      // a hint that does not fit is shortened
+        off_tile = (lz * rec_bytes + 32 * 16 + 15) & ~15;           // + per-group skew
+        warp_smem = off_tile + lz * nvec * 16;
+        smem = (size_t)warp_smem * kWarps;
+        if (smem <= 160 * 1024 || lz == 1) break;
+        lz = (lz + 1) / 2;
+    }
+    if (smem > 220 * 1024)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: V=%d needs %zu bytes of shared memory", V, smem);
+
+    const char *packed;
     if (feat_layout == MVHMR_LAYOUT_NCHW) {
         const size_t need = mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);
         if (!ws || ws_bytes < need)
             return fail(MVHMR_ERR_WORKSPACE, "unproject_aggregate: workspace of %zu bytes required, got %zu", need, ws_bytes);
         if ((uintptr_t)ws & 15) return fail(MVHMR_ERR_WORKSPACE, "unproject_aggregate: workspace must be 16-byte aligned");
         // only the samples of the shard window are packed
-        const size_t per_sample_in = (size_t)V * C * H * W * (feat_dtype == MVHMR_BF16 ? 2 : 4);
+        const size_t per_sample_in = (size_t)V * C * H * W * (bf ? 2 : 4);
         const size_t per_sample_pk = need / (size_t)B;
         int rc = mvhmr_pack_features((const char *)feats + per_sample_in * b0, feat_dtype,
                                      (char *)ws + per_sample_pk * b0, (b1 - b0) * V, C, H, W, stream);
         if (rc != MVHMR_OK) return rc;
-        packed = (const uint4 *)ws;
+        packed = (const char *)ws;
     } else {
         if ((uintptr_t)feats & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: packed features must be 16-byte aligned");
-        packed = (const uint4 *)feats;
+        packed = (const char *)feats;
     }
 
     UnprojParams p;
     p.packed = packed; p.proj = proj; p.coord = coord; p.out = out;
     p.n0 = n0; p.n1 = n1; p.n_origin = n_origin; p.n_extent = n_extent;
-    p.Wp = W + 2 * kBorder; p.plane = (long long)(H + 2 * kBorder) * p.Wp;
-    p.V = V; p.C = C; p.W = W; p.H = H; p.chunks = chunks; p.b0 = b0;
+    p.Wp = W + 2 * kBorder;
+    p.nchunks = nchunks;
+    p.lpb = ilog2_exact(nchunks) + 4;
+    p.plane_bytes = ((long long)(H + 2 * kBorder) * p.Wp) << p.lpb;
+    p.V = V; p.VP = VP; p.C = C; p.W = W; p.H = H; p.b0 = b0; p.nb = b1 - b0;
     p.gx = gx; p.gy = gy; p.gz = gz;
-    p.ltx = ilog2_exact(TX); p.lty = ilog2_exact(TY); p.ltz = ilog2_exact(TZ);
     const long long yz = (long long)gy * gz;
     p.x_lo = (int)(n0 / yz);
-    const int x_hi = (int)((n1 - 1) / yz);
-    const int tiles_x = (x_hi - p.x_lo + TX) / TX;
-    p.tiles_y = (gy + TY - 1) / TY; p.tiles_z = (gz + TZ - 1) / TZ;
+    p.nx = (int)((n1 - 1) / yz) - p.x_lo + 1;
+    p.lz = lz; p.nseg = (gz + lz - 1) / lz;
+    p.warp_smem = warp_smem; p.rec_bytes = rec_bytes; p.off_tile = off_tile;
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
-    const long long tiles = (long long)tiles_x * p.tiles_y * p.tiles_z;
-    if (tiles > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: volume too large");
-    dim3 grid((unsigned)tiles, (unsigned)(b1 - b0));
-    const size_t smem = (size_t)V * 12 * sizeof(float);
-    const bool bf = feat_dtype == MVHMR_BF16;
-    if (V <= 4) {
-        if (bf) launch_method<4, true, false>(method, grid, smem, st, p);
-        else launch_method<4, false, false>(method, grid, smem, st, p);
-    } else if (V <= 8) {
-        if (bf) launch_method<8, true, false>(method, grid, smem, st, p);
-        else launch_method<8, false, false>(method, grid, smem, st, p);
-    } else {
-        if (bf) launch_method<8, true, true>(method, grid, smem, st, p);
-        else launch_method<8, false, true>(method, grid, smem, st, p);
-    }
+    p.rH = 1.0f / (float)H; p.rW = 1.0f / (float)W;
+    if ((long long)p.nb * p.nseg > 65535 || gy > 65535)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: grid too large (samples*segments=%lld, gy=%d); split the call",
+                    (long long)p.nb * p.nseg, gy);
+    const dim3 grid((p.nx + kWarps - 1) / kWarps, gy, p.nb * p.nseg);
+    cudaError_t e;
+    if (V == 4)
+        e = bf ? launch_lpb<4, true, MVHMR_CACHE4, true>(method, grid, smem, st, p) : launch_lpb<4, true, MVHMR_CACHE4, false>(method, grid, smem, st, p);
+    else if (V < 4)
+        e = bf ? launch_lpb<4, false, MVHMR_CACHE4, true>(method, grid, smem, st, p) : launch_lpb<4, false, MVHMR_CACHE4, false>(method, grid, smem, st, p);
+    else if (V == 8)
+        e = bf ? launch_lpb<8, true, false, true>(method, grid, smem, st, p) : launch_lpb<8, true, false, false>(method, grid, smem, st, p);
+    else
+        e = bf ? launch_lpb<8, false, false, true>(method, grid, smem, st, p) : launch_lpb<8, false, false, false>(method, grid, smem, st, p);
+    if (e != cudaSuccess) return fail(MVHMR_ERR_CUDA, "unproject_kernel: %s", cudaGetErrorString(e));
     return check_launch("unproject_kernel");
 }

@@ -38,8 +38,8 @@ for name in ['unproj_ragged', 'unproj_edge', 'unproj_bf16']:
             o = agg.unprojection(ft.bfloat16(), torch.from_numpy(z['proj']).to(dev), torch.from_numpy(z['coord_volumes']).to(dev), m).cpu().numpy()
             print(name, m, '(bf16 storage) rel', rel(o, z['out_' + m]), 'biteq', float((o == z['out_' + m]).mean()))
 
-tiles = [None, '8,1,32', '4,2,32', '2,4,32', '1,8,32', '16,1,16', '8,2,16', '4,4,16', '8,4,8', '4,8,8', '16,2,8']
-for cfgname in ['cfg2', 'cfg3', 'cfg4']:
+tiles = [None, '32', '16']
+for cfgname in ['cfg2', 'cfg3', 'cfg4', 'cfg5']:
     w = syn.CONFIGS[cfgname]
     f, P, cv, c = syn.make_inputs(w)
     fd = f.to(dev); Pd = P.to(dev); cvd = cv.to(dev)
@@ -47,11 +47,11 @@ for cfgname in ['cfg2', 'cfg3', 'cfg4']:
     out = torch.empty((w.B, w.C, w.G, w.G, w.G), device=dev)
     ab = w.algorithmic_bytes()
     for tile in tiles:
-        if tile is None: os.environ.pop('MVHMR_TILE', None)
-        else: os.environ['MVHMR_TILE'] = tile
+        if tile is None: os.environ.pop('MVHMR_LZ', None)
+        else: os.environ['MVHMR_LZ'] = tile
         tmin, tmed = time_fn(lambda: agg.unprojection(fd, Pd, cvd, w.method, out=out))
         print(f'{cfgname} tile={tile}: min {tmin*1e3:.1f} us med {tmed*1e3:.1f} us  {w.vcv/tmin/1e6:.0f} Gvcv/s  roofline {ab/tmin/1e6/6543.1*100:.1f}%', flush=True)
-    os.environ.pop('MVHMR_TILE', None)
+    os.environ.pop('MVHMR_LZ', None)
     packed = agg.pack_features(fd)
     tmin, tmed = time_fn(lambda: agg.unprojection(fd, Pd, cvd, w.method, out=out, packed=packed))
     print(f'{cfgname} prepacked: min {tmin*1e3:.1f} us')

@@ -35,10 +35,11 @@ def test_library_exports_every_declared_symbol(built_lib):
 def test_abi_version_and_sizes(built_lib):
     L = _lib.load()
     assert L.mvhmr_abi_version() == 1
-    # (B*V, chunks, H+4, W+4) texels of 16 bytes
+    # (B*V, H+4, W+4, vectors) with 16-byte channel vectors, count padded to a power of two
     assert L.mvhmr_packed_bytes(_lib.F32, 32, 32, 96, 96) == 32 * 8 * 100 * 100 * 16
     assert L.mvhmr_packed_bytes(_lib.BF16, 32, 32, 96, 96) == 32 * 4 * 100 * 100 * 16
     assert L.mvhmr_packed_bytes(_lib.F32, 2, 5, 7, 9) == 2 * 2 * 11 * 13 * 16
+    assert L.mvhmr_packed_bytes(_lib.F32, 1, 20, 7, 9) == 8 * 11 * 13 * 16
     assert L.mvhmr_packed_bytes(7, 2, 5, 7, 9) == 0
     assert L.mvhmr_unproject_workspace_bytes(_lib.F32, _lib.LAYOUT_PACKED, 8, 4, 32, 96, 96) == 0
     assert L.mvhmr_soft_argmax3d_num_slices(64 ** 3) == 128
@@ -60,7 +61,7 @@ def test_argument_validation_needs_no_gpu(built_lib):
     assert rc == _lib.ERR_WORKSPACE
     with pytest.raises(RuntimeError, match="workspace"):
         _lib.check(rc)
-    rc = L.mvhmr_unproject_aggregate(*args, _lib.SUM, 0, 1, 0, 32 ** 3, 0, 32 ** 3, 3 | (5 << 8) | (7 << 16),
+    rc = L.mvhmr_unproject_aggregate(*args, _lib.SUM, 0, 1, 0, 32 ** 3, 0, 32 ** 3, 65,
                                      one, 1 << 30, None)
     assert rc == _lib.ERR_INVALID_ARGUMENT and b"tile_hint" in L.mvhmr_last_error()
     assert L.mvhmr_soft_argmax3d(one, one, one, 1, 1, 64, None, 0, None) == _lib.ERR_WORKSPACE

@@ -105,12 +105,12 @@ def test_ragged_shapes(B, V, C, H, W, G, method):
     check_volume(got, oracle.unprojection(f, P, cv, method), method)
 
 
-@pytest.mark.parametrize("tile", ["8,1,32", "1,8,32", "4,4,16", "2,16,8", "64,1,4", "2,1,128"])
-def test_tile_shapes_do_not_change_results(monkeypatch, tile):
+@pytest.mark.parametrize("lz", ["1", "5", "8", "24", "32"])
+def test_z_segment_length_does_not_change_results(monkeypatch, lz):
     w = syn.Workload("t", B=2, V=4, C=8, H=32, W=32, G=24)
     f, P, cv, _ = syn.make_inputs(w, seed=3)
     base = agg.unprojection(*cuda(f, P, cv), "softmax")
-    monkeypatch.setenv("MVHMR_TILE", tile)
+    monkeypatch.setenv("MVHMR_LZ", lz)
     assert torch.equal(agg.unprojection(*cuda(f, P, cv), "softmax"), base)
 
 
@@ -213,6 +213,8 @@ def test_volume_generator_module(golden, case):
     vg.load_state_dict({"process_feature.0.weight": torch.from_numpy(z["conv_weight"]),
                         "process_feature.0.bias": torch.from_numpy(z["conv_bias"])})
     vg.train(bool(z["training"]))
+    torch.backends.cudnn.allow_tf32 = False          # the 1x1 conv is the reference's own torch op: keep it fp32
+    torch.backends.cuda.matmul.allow_tf32 = False
     seen = {}
     real = agg.unprojection
 
@@ -234,11 +236,11 @@ def test_volume_generator_module(golden, case):
         assert np.allclose(seen["coord"].cpu().numpy(), z["used_coord_volumes"], rtol=0, atol=1e-3)
     else:
         assert np.array_equal(seen["coord"].cpu().numpy(), z["used_coord_volumes"])      # bit-exact grid
-    # the 1x1 conv is cuDNN (tensor cores may be TF32-free but not bit-equal to MKL): compare
-    # the fused op on the reference's own squeezed features, then the module end to end
+    # the 1x1 conv is cuDNN (fp32, but not bit-equal to MKL): compare the fused op on the
+    # reference's own squeezed features, then the module end to end
     fused = agg.unprojection(*cuda(z["used_features"], z["used_proj"], z["used_coord_volumes"]), "softmax")
     assert rel_l2(fused.cpu().numpy(), z["volumes"]) < OUR_TOL_SOFTMAX
-    assert rel_l2(vol.cpu().numpy(), z["volumes"]) < 1e-4
+    assert rel_l2(vol.cpu().numpy(), z["volumes"]) < SPEC_TOL_FP32
     assert vol.shape == z["volumes"].shape and vol.dtype == torch.float32
 
 
