@@ -284,7 +284,7 @@ def main():
             "e2e": {"value": units / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                     "path": "pinned host -> unprojection() -> soft_argmax_3d() -> host"},
-            "gpu_launches": launches,
+            "gpu_launches": launches * world,
             "clocks": sampler.summary(),
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -46,6 +46,7 @@ constexpr int kBorder = 2;
 #endif
 constexpr int kWarps = MVHMR_WARPS;       // warps per CTA: consecutive x planes share their texel footprint in L1
 constexpr int kLzMax = 32;                // voxels of one warp task (z segment): one per lane in phase A
+constexpr int kYRows = 1;                 // consecutive y rows walked by one CTA
 constexpr int kVecPass = 32;              // 16-byte channel vectors handled per pass (at most one per lane)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: a float add rounds to integer
@@ -337,7 +338,6 @@ unproject_kernel(const UnprojParams p)
     const int xi = blockIdx.x * kWarps + warp;
     if (xi >= p.nx) return;                          // warps are independent: no block-level barrier anywhere
     const int vx = p.x_lo + xi;
-    const int vy = blockIdx.y;
     const int seg = blockIdx.z % (unsigned)p.nseg;
     const int b = p.b0 + blockIdx.z / (unsigned)p.nseg;
 
@@ -361,6 +361,10 @@ unproject_kernel(const UnprojParams p)
     const int z0 = seg * p.lz;
     const int zn = min(p.lz, p.gz - z0);             // voxels in this segment (<= 32)
     const int steps = (zn + ngroups - 1) >> (5 - lpv_log);
+    // consecutive y rows are walked by the same CTA: their footprints share texel rows, so
+    // most of a row's first-touch L1 misses are paid once per kYRows rows
+    for (int vy = blockIdx.y * kYRows; vy < min(p.gy, (int)(blockIdx.y + 1) * kYRows); ++vy) {
+
     const long long nrow = ((long long)vx * p.gy + vy) * p.gz + z0;   // flattened index of the first voxel
     const long long nme = nrow + lane;               // the voxel this lane projects / writes
     const bool mine = (lane < zn) && (nme >= p.n0) && (nme < p.n1);
@@ -386,7 +390,10 @@ unproject_kernel(const UnprojParams p)
         const char *vbase[VMAX];
 #pragma unroll
         for (int v = 0; v < VMAX; ++v) vbase[v] = lane_base + (size_t)v * p.plane_bytes;
-        constexpr int TV = VMAX < 4 ? VMAX : 4;      // views whose texels are in registers at once
+#ifndef MVHMR_TV
+#define MVHMR_TV 4
+#endif
+        constexpr int TV = CACHE ? (VMAX < 4 ? VMAX : 4) : (VMAX < MVHMR_TV ? VMAX : MVHMR_TV);   // views whose texels are in registers at once
         uint4 tex[TV][4];
         int cur[TV];
 #pragma unroll
@@ -395,14 +402,20 @@ unproject_kernel(const UnprojParams p)
         // gathers of up to TV views [v0, v0+nv) for the voxel whose record is r; returns false if
         // the voxel is outside the shard window
         auto gather = [&](const unsigned char *r, int v0, int nv) -> bool {
-            const int4 o4 = *reinterpret_cast<const int4 *>(r + wbytes + v0 * 4);
-            const int off[4] = {o4.x, o4.y, o4.z, o4.w};
+            int off[4];
+            if (TV == 4) {
+                const int4 o4 = *reinterpret_cast<const int4 *>(r + wbytes + v0 * 4);
+                off[0] = o4.x; off[1] = o4.y; off[2] = o4.z; off[3] = o4.w;
+            } else {
+#pragma unroll
+                for (int v = 0; v < TV; ++v) off[v] = *reinterpret_cast<const int *>(r + wbytes + (v0 + v) * 4);
+            }
 #pragma unroll
             for (int v = 0; v < TV; ++v) {
                 if (EXACT || v < nv) {
                     const int o = max(off[v], 0);
                     if (!CACHE || o != cur[v]) {
-                        const char *q0 = (single && VMAX <= 4 ? vbase[v % VMAX] : lane_base + (size_t)(v0 + v) * p.plane_bytes)
+                        const char *q0 = (single ? vbase[(v0 + v) % VMAX] : lane_base + (size_t)(v0 + v) * p.plane_bytes)
                                          + ((unsigned)o << lpb);
                         const char *q1 = q0 + row;
                         tex[v][0] = __ldg(reinterpret_cast<const uint4 *>(q0));
@@ -495,6 +508,7 @@ unproject_kernel(const UnprojParams p)
             }
         }
         __syncwarp();
+    }
     }
 }
 
@@ -689,7 +703,7 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
     int off_tile, warp_smem;
     size_t smem;
     for (;;) {                                                      // a hint that does not fit is shortened
-        off_tile = (lz * rec_bytes + 32 * 16 + 15) & ~15;           // + per-group skew
+        off_tile = (lz * rec_bytes + (32 / nch_pass) * 16 + 15) & ~15;   // + per-group skew
         warp_smem = off_tile + lz * nvec * 16;
         smem = (size_t)warp_smem * kWarps;
         if (smem <= 160 * 1024 || lz == 1) break;
@@ -736,7 +750,7 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
     if ((long long)p.nb * p.nseg > 65535 || gy > 65535)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: grid too large (samples*segments=%lld, gy=%d); split the call",
                     (long long)p.nb * p.nseg, gy);
-    const dim3 grid((p.nx + kWarps - 1) / kWarps, gy, p.nb * p.nseg);
+    const dim3 grid((p.nx + kWarps - 1) / kWarps, (gy + kYRows - 1) / kYRows, p.nb * p.nseg);
     cudaError_t e;
     if (V == 4)
         e = bf ? launch_lpb<4, true, MVHMR_CACHE4, true>(method, grid, smem, st, p) : launch_lpb<4, true, MVHMR_CACHE4, false>(method, grid, smem, st, p);
