@@ -66,6 +66,7 @@ struct UnprojParams {
     int gx, gy, gz;
     int x_lo, nx;          // x planes touched by [n0,n1)
     int lz, nseg;          // z segment length (<= kLzMax) and segments per z row
+    unsigned ntasks, nxb;  // warp tasks; x planes per row rounded up to a multiple of kWarps
     int warp_smem;         // bytes of shared memory per warp
     int rec_bytes;         // bytes of one voxel record: V x float4 weights, then VP x int offsets
     int off_tile;          // byte offset of the output tile inside a warp's smem
@@ -311,7 +312,11 @@ struct Fuse2 {
     __device__ __forceinline__ f2 result(float Vf) const
     {
         if (METHOD == MVHMR_SUM) return upk(a);
-        if (METHOD == MVHMR_MEAN) { f2 r = upk(a); r.x = __fdiv_rn(r.x, Vf); r.y = __fdiv_rn(r.y, Vf); return r; }
+        if (METHOD == MVHMR_MEAN) {                    // x / V, correctly rounded (see div_const2)
+            f2 r = upk(a), q;
+            div_const2(r.x, r.y, Vf, 1.0f / Vf, Vf, 1.0f / Vf, q.x, q.y);
+            return q;
+        }
         if (METHOD == MVHMR_MAX) { f2 r; r.x = m0; r.y = m1; return r; }
         const f2 s = upk(S);
         return upk(mul2(a, pk(rcp_approx(s.x), rcp_approx(s.y))));
@@ -335,12 +340,6 @@ unproject_kernel(const UnprojParams p)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NP = BF16 ? 4 : 2;                 // channel pairs per lane per pass
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int xi = blockIdx.x * kWarps + warp;
-    if (xi >= p.nx) return;                          // warps are independent: no block-level barrier anywhere
-    const int vx = p.x_lo + xi;
-    const int seg = blockIdx.z % (unsigned)p.nseg;
-    const int b = p.b0 + blockIdx.z / (unsigned)p.nseg;
-
     unsigned char *recs = smem_raw + (size_t)warp * p.warp_smem;
     // per-voxel records: V x float4 bilinear weights, then VP x int pixel offsets (-1: voxel not
     // in the shard window).  Records of different lane groups are skewed by 16 bytes so that
@@ -358,13 +357,21 @@ unproject_kernel(const UnprojParams p)
     const int wbytes = EXACT ? VMAX * 16 : p.V * 16;
     const int rec_bytes = EXACT ? VMAX * 16 + ((VMAX + 3) & ~3) * 4 : p.rec_bytes;
 
+    // Persistent CTAs: tasks are numbered x-fastest and dealt out in rounds of gridDim.x * kWarps,
+    // so the warps of a CTA always work on consecutive x planes of one (sample, z segment, y) row
+    // while drifting apart in phase (projection / gathers / stores overlap across warps).
+    for (unsigned task = blockIdx.x * kWarps + warp; task < p.ntasks; task += gridDim.x * kWarps) {
+    unsigned t = task / p.nxb;                       // task -> (b, z segment, y, x block, x in block)
+    const unsigned xblk = task - t * p.nxb;
+    const int vy = (int)(t % (unsigned)p.gy); t /= (unsigned)p.gy;
+    const int seg = (int)(t % (unsigned)p.nseg);
+    const int b = p.b0 + (int)(t / (unsigned)p.nseg);
+    if ((int)xblk >= p.nx) continue;                 // padding of the last x block
+    const int vx = p.x_lo + (int)xblk;
     const int z0 = seg * p.lz;
     const int zn = min(p.lz, p.gz - z0);             // voxels in this segment (<= 32)
     const int steps = (zn + ngroups - 1) >> (5 - lpv_log);
-    // consecutive y rows are walked by the same CTA: their footprints share texel rows, so
-    // most of a row's first-touch L1 misses are paid once per kYRows rows
-    for (int vy = blockIdx.y * kYRows; vy < min(p.gy, (int)(blockIdx.y + 1) * kYRows); ++vy) {
-
+    {
     const long long nrow = ((long long)vx * p.gy + vy) * p.gz + z0;   // flattened index of the first voxel
     const long long nme = nrow + lane;               // the voxel this lane projects / writes
     const bool mine = (lane < zn) && (nme >= p.n0) && (nme < p.n1);
@@ -509,7 +516,8 @@ unproject_kernel(const UnprojParams p)
         }
         __syncwarp();
     }
-    }
+    }   // task body
+    }   // persistent task loop
 }
 
 // NCHW -> pixel-major padded planes.  One CTA per padded row: channel planes are
@@ -747,10 +755,16 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
     p.rH = 1.0f / (float)H; p.rW = 1.0f / (float)W;
-    if ((long long)p.nb * p.nseg > 65535 || gy > 65535)
-        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: grid too large (samples*segments=%lld, gy=%d); split the call",
-                    (long long)p.nb * p.nseg, gy);
-    const dim3 grid((p.nx + kWarps - 1) / kWarps, (gy + kYRows - 1) / kYRows, p.nb * p.nseg);
+    p.nxb = (unsigned)((p.nx + kWarps - 1) / kWarps * kWarps);
+    const long long ntasks = (long long)p.nb * p.nseg * gy * p.nxb;
+    if (ntasks > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: too many z rows in one call");
+    p.ntasks = (unsigned)ntasks;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned ctas = (unsigned)((ntasks + kWarps - 1) / kWarps);
+    const unsigned resident = (unsigned)sms * MVHMR_MINBLOCKS;       // one CTA (or MINBLOCKS) per SM, persistent
+    const dim3 grid(ctas < resident ? ctas : resident);
     cudaError_t e;
     if (V == 4)
         e = bf ? launch_lpb<4, true, MVHMR_CACHE4, true>(method, grid, smem, st, p) : launch_lpb<4, true, MVHMR_CACHE4, false>(method, grid, smem, st, p);
