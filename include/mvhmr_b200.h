@@ -131,6 +131,40 @@ int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int feat_layout
                               long long n_origin, long long n_extent,
                               unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
 
+/* The cuboid grid of models/aggregation.py:135-187 as a descriptor instead of a
+ * materialised (B,Gx,Gy,Gz,3) tensor: voxel (x,y,z) of sample b sits at
+ *   rot[b] * ((pos + step*(x,y,z)) - centers[b]) + centers[b]
+ * exactly as mvhmr_build_coord_volumes would write it (same fp32 roundings). */
+typedef struct mvhmr_grid {
+    const float *centers; /* device, (B,3)                                    */
+    const float *rot;     /* device, (B,3,3) row-major, identity in eval mode */
+    float pos[3];         /* -side/2 per axis, rounded to fp32                */
+    float step[3];        /* side/(G-1) per axis, rounded to fp32             */
+} mvhmr_grid_t;
+
+/* mvhmr_unproject_aggregate with the coordinates generated in registers from
+ * `grid` (host pointer to the descriptor, read during the call): saves the
+ * 12 B/voxel write and read of the coord volume.
+ * Requires the true volume shape in gx,gy,gz.  Results are bit-identical to
+ * building the volume first. */
+int mvhmr_unproject_aggregate_grid(const void *feats, int feat_dtype, int feat_layout,
+                                   const float *proj, const mvhmr_grid_t *grid, float *out,
+                                   int B, int V, int C, int H, int W,
+                                   int gx, int gy, int gz, int method,
+                                   int b0, int b1, long long n0, long long n1,
+                                   long long n_origin, long long n_extent,
+                                   unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
+
+/* Backward of mvhmr_unproject_aggregate w.r.t. the feature maps (the gradient
+ * torch autograd produces for models/aggregation.py:20-87; training goes through
+ * this op, train.py:110).  grad_out (B,C,N) fp32; feats (B,V,C,H,W) NCHW fp32 or
+ * bf16 (re-sampled to rebuild the fusion Jacobian); grad_feats (B,V,C,H,W) fp32,
+ * ZEROED BY THE CALLER, accumulated with atomics (summation order, and therefore
+ * the last bits, vary from run to run).  V <= 64. */
+int mvhmr_unproject_aggregate_backward(const float *grad_out, const void *feats, int feat_dtype,
+                                       const float *proj, const float *coord, float *grad_feats,
+                                       int B, int V, int C, int H, int W, long long N, int method, void *stream);
+
 /* ---- 3-D soft-argmax ------------------------------------------------------ */
 /* Not in the reference; upstream definition
  * (Learnable-Triangulation integrate_tensor_3d_with_coordinates, cited by URL at

@@ -32,12 +32,23 @@ SIGNATURES = {
     "mvhmr_unproject_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mvhmr_unproject_aggregate": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                        _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
+    "mvhmr_unproject_aggregate_grid": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                            _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
+    "mvhmr_unproject_aggregate_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp]),
     "mvhmr_soft_argmax3d_num_slices": (_i, [_ll]),
     "mvhmr_soft_argmax3d_workspace_bytes": (_sz, [_i, _i, _ll]),
     "mvhmr_soft_argmax3d": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _sz, _vp]),
     "mvhmr_soft_argmax3d_partials": (_i, [_vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp]),
     "mvhmr_soft_argmax3d_finalize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
 }
+
+
+
+class Grid(ctypes.Structure):
+    """mvhmr_grid_t"""
+    _fields_ = [("centers", ctypes.c_void_p), ("rot", ctypes.c_void_p),
+                ("pos", ctypes.c_float * 3), ("step", ctypes.c_float * 3)]
+
 
 _lib = None
 

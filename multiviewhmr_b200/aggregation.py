@@ -11,6 +11,7 @@ per-view `F.grid_sample` loop:
 All tensors must be CUDA tensors; the library behind `_lib` is the only
 implementation (no eager fallback).
 """
+import ctypes
 import os
 
 import numpy as np
@@ -81,11 +82,20 @@ def unprojection(features, proj_matricies, coord_volumes, aggregation_method='so
         from .autograd import unprojection_with_grad
         return unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method)
     gx, gy, gz = (int(v) for v in coord_volumes.shape[1:4])
+    coord = coord_volumes.detach().float().contiguous()
+    return _launch_unprojection(features, proj_matricies, (gx, gy, gz), aggregation_method, window, out, packed,
+                                coord=coord)
+
+
+def _launch_unprojection(features, proj_matricies, shape, aggregation_method, window, out, packed,
+                         coord=None, grid=None):
+    dev = features.device
+    B, V, C, H, W = features.shape
+    gx, gy, gz = shape
     N = gx * gy * gz
     dt = _feat_dtype(features)
     L = _lib.load()
     proj = proj_matricies.detach().float().contiguous()
-    coord = coord_volumes.detach().float().contiguous()
     if out is None:
         out = torch.empty((B, C, gx, gy, gz), dtype=torch.float32, device=dev)
     elif (tuple(out.shape) != (B, C, gx, gy, gz) or out.dtype != torch.float32
@@ -103,11 +113,53 @@ def unprojection(features, proj_matricies, coord_volumes, aggregation_method='so
             feats, layout, ws_bytes, ws_ptr = packed, _lib.LAYOUT_PACKED, 0, None
             if packed.numel() != L.mvhmr_packed_bytes(dt, B * V, C, H, W):
                 raise ValueError("packed features do not match the shape of `features`")
-        _lib.check(L.mvhmr_unproject_aggregate(
-            _lib.ptr(feats), dt, layout, _lib.ptr(proj), _lib.ptr(coord), _lib.ptr(out),
-            B, V, C, H, W, gx, gy, gz, _lib.METHODS[aggregation_method],
-            b0, b1, n0, n1, 0, N, _tile_hint(), ws_ptr, ws_bytes, _lib.stream_ptr(dev)))
+        tail = (B, V, C, H, W, gx, gy, gz, _lib.METHODS[aggregation_method],
+                b0, b1, n0, n1, 0, N, _tile_hint(), ws_ptr, ws_bytes, _lib.stream_ptr(dev))
+        if grid is None:
+            _lib.check(L.mvhmr_unproject_aggregate(_lib.ptr(feats), dt, layout, _lib.ptr(proj), _lib.ptr(coord),
+                                                   _lib.ptr(out), *tail))
+        else:
+            _lib.check(L.mvhmr_unproject_aggregate_grid(_lib.ptr(feats), dt, layout, _lib.ptr(proj),
+                                                        ctypes.byref(grid), _lib.ptr(out), *tail))
     return out
+
+
+def unprojection_grid(features, proj_matricies, centers, rotations, volume_size, cuboid_side,
+                      aggregation_method='softmax', window=None, out=None, packed=None):
+    """`unprojection` over the cuboid grid of `models/aggregation.py:135-187` without
+    materialising it: the voxel coordinates are generated inside the kernel from the
+    per-sample centre and rotation (same fp32 roundings as `build_coord_volumes`, so the
+    result is bit-identical to build + unproject).  centers (B,3), rotations (B,3,3): host
+    float32 arrays.  Not in the reference."""
+    if aggregation_method not in _lib.METHODS:
+        raise ValueError("Unknown aggregation_method: {}".format(aggregation_method))
+    dev = _lib.require_cuda(features, proj_matricies)
+    B, V = features.shape[:2]
+    if features.dim() != 5 or tuple(proj_matricies.shape) != (B, V, 3, 4):
+        raise ValueError("expected features (B,V,C,H,W) and proj_matricies (B,V,3,4), got %s and %s"
+                         % (tuple(features.shape), tuple(proj_matricies.shape)))
+    if torch.is_grad_enabled() and features.requires_grad:
+        coord_volumes = build_coord_volumes(centers, rotations, volume_size, cuboid_side, dev)
+        return unprojection(features, proj_matricies, coord_volumes, aggregation_method)
+    G = int(volume_size)
+    dev_buf = _grid_buffer(centers, rotations, dev)
+    grid = _lib.Grid()
+    grid.centers = dev_buf.data_ptr()
+    grid.rot = dev_buf.data_ptr() + B * 3 * 4
+    pos = np.float32(0.0 - cuboid_side / 2)
+    step = np.float32(cuboid_side / (G - 1))
+    for k in range(3):
+        grid.pos[k] = float(pos)
+        grid.step[k] = float(step)
+    return _launch_unprojection(features, proj_matricies, (G, G, G), aggregation_method, window, out, packed,
+                                grid=grid)
+
+
+def _grid_buffer(centers, rotations, device):
+    """One H2D copy: B centres (B,3) followed by B rotations (B,9), fp32."""
+    centers = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1)
+    rotations = np.ascontiguousarray(rotations, dtype=np.float32).reshape(-1)
+    return torch.from_numpy(np.concatenate([centers, rotations])).to(device)
 
 
 def soft_argmax_3d(volumes, coord_volumes):
@@ -225,6 +277,7 @@ class VolumeGenerator(nn.Module):
         self.use_triangulation = use_triangulation
         self.kind = kind
         self.dataset = dataset
+        self.fuse_grid = True       # not a reference attribute: build the cuboid grid inside the fused kernel
         self.to(device)
 
     def _projections(self, batch, images_shape, features_shape, n_views, batch_size):
@@ -265,12 +318,14 @@ class VolumeGenerator(nn.Module):
                     proj_org[b], images_center).numpy()
             else:
                 centers[b] = np.asarray(batch['keypoints_3d'][b])[6, :3]          # `:180-181`
-        coord_volumes = build_coord_volumes(centers, rots, self.volume_size, self.cuboid_side, device)
-
         features = features.view(-1, *features.shape[2:])
         features = self.process_feature(features)
         features = features.view(batch_size, n_views, *features.shape[1:])
 
+        if self.fuse_grid:      # coordinates generated inside the kernel, bit-identical to the two-step path
+            return unprojection_grid(features, proj, centers, rots, self.volume_size, self.cuboid_side,
+                                     aggregation_method=self.aggregation_method)
+        coord_volumes = build_coord_volumes(centers, rots, self.volume_size, self.cuboid_side, device)
         return unprojection(features, proj, coord_volumes, aggregation_method=self.aggregation_method)
 
 

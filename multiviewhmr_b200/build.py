@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmvhmr_b200.so")
-SOURCES = ["abi.cu", "geometry.cu", "unproject.cu", "softargmax.cu"]
+SOURCES = ["abi.cu", "geometry.cu", "unproject.cu", "softargmax.cu", "backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static"]
 

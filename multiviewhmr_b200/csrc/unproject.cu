@@ -54,7 +54,10 @@ constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: a float add rounds to i
 struct UnprojParams {
     const char *packed;    // (B*V, Hp, Wp, CP) pixel-major planes
     const float *proj;     // (B, V, 3, 4)
-    const float *coord;    // (B, n_extent, 3): voxels [n_origin, n_origin + n_extent)
+    const float *coord;    // (B, n_extent, 3): voxels [n_origin, n_origin + n_extent); NULL = generate
+    const float *centers;  // (B, 3)   } only when coord == NULL: the grid of
+    const float *rot;      // (B, 3, 3) } models/aggregation.py:135-187 is built in registers
+    float gpos[3], gstep[3];
     float *out;            // (B, C, n_extent)
     long long n0, n1;      // voxels computed by this launch
     long long n_origin, n_extent;
@@ -378,8 +381,23 @@ unproject_kernel(const UnprojParams p)
 
     // ---- phase A: one voxel per lane, projected through every view ----
     if (lane < zn) {
-        const float *xyz = p.coord + ((size_t)b * p.n_extent + (mine ? nme - p.n_origin : 0)) * 3;
-        const float X = mine ? __ldg(xyz) : 0.0f, Y = mine ? __ldg(xyz + 1) : 0.0f, Z = mine ? __ldg(xyz + 2) : 0.0f;
+        float X = 0.0f, Y = 0.0f, Z = 0.0f;
+        if (p.coord) {
+            if (mine) {
+                const float *xyz = p.coord + ((size_t)b * p.n_extent + (nme - p.n_origin)) * 3;
+                X = __ldg(xyz); Y = __ldg(xyz + 1); Z = __ldg(xyz + 2);
+            }
+        } else {
+            // same arithmetic as coord_volume_kernel (bit-identical coordinates, never stored)
+            const float *c = p.centers + 3 * b, *R = p.rot + 9 * b;
+            const float c0 = __ldg(c), c1 = __ldg(c + 1), c2 = __ldg(c + 2);
+            const float d0 = __fsub_rn(__fadd_rn(p.gpos[0], __fmul_rn(p.gstep[0], (float)vx)), c0);
+            const float d1 = __fsub_rn(__fadd_rn(p.gpos[1], __fmul_rn(p.gstep[1], (float)vy)), c1);
+            const float d2 = __fsub_rn(__fadd_rn(p.gpos[2], __fmul_rn(p.gstep[2], (float)(z0 + lane))), c2);
+            X = __fadd_rn(rot_row(__ldg(R), __ldg(R + 1), __ldg(R + 2), d0, d1, d2), c0);
+            Y = __fadd_rn(rot_row(__ldg(R + 3), __ldg(R + 4), __ldg(R + 5), d0, d1, d2), c1);
+            Z = __fadd_rn(rot_row(__ldg(R + 6), __ldg(R + 7), __ldg(R + 8), d0, d1, d2), c2);
+        }
         unsigned char *rec = recs + lane * rec_bytes + (lane / steps) * 16;
         const float4 *Pb = reinterpret_cast<const float4 *>(p.proj + (size_t)b * p.V * 12);
         for (int v = 0; v < p.V; ++v) {
@@ -657,13 +675,13 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     return check_launch("pack_kernel");
 }
 
-extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int feat_layout,
-                                         const float *proj, const float *coord, float *out,
-                                         int B, int V, int C, int H, int W,
-                                         int gx, int gy, int gz, int method,
-                                         int b0, int b1, long long n0, long long n1,
-                                         long long n_origin, long long n_extent,
-                                         unsigned tile_hint, void *ws, size_t ws_bytes, void *stream)
+static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
+                          const float *proj, const float *coord, const mvhmr_grid_t *grid_desc, float *out,
+                          int B, int V, int C, int H, int W,
+                          int gx, int gy, int gz, int method,
+                          int b0, int b1, long long n0, long long n1,
+                          long long n_origin, long long n_extent,
+                          unsigned tile_hint, void *ws, size_t ws_bytes, void *stream)
 {
     if (method < MVHMR_SUM || method > MVHMR_SOFTMAX)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "Unknown aggregation_method: %d", method);
@@ -685,7 +703,9 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
     if (tile_hint > (unsigned)kLzMax)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: tile_hint %u (z-segment length) must be <= %d", tile_hint, kLzMax);
     if (b0 == b1 || n0 == n1) return MVHMR_OK;
-    if (!feats || !proj || !coord || !out) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
+    if (!feats || !proj || !out || (!coord && !grid_desc)) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
+    if (grid_desc && (!grid_desc->centers || !grid_desc->rot))
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_grid: null centers / rot");
     if ((long long)(H + 4) * (W + 4) * nchunks_of(feat_dtype, C) * 16 >= (1LL << 31))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: one padded feature map must stay below 2 GiB");
     if ((uintptr_t)proj & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: proj must be 16-byte aligned");
@@ -740,6 +760,12 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
 
     UnprojParams p;
     p.packed = packed; p.proj = proj; p.coord = coord; p.out = out;
+    p.centers = grid_desc ? grid_desc->centers : nullptr;
+    p.rot = grid_desc ? grid_desc->rot : nullptr;
+    for (int k = 0; k < 3; ++k) {
+        p.gpos[k] = grid_desc ? grid_desc->pos[k] : 0.0f;
+        p.gstep[k] = grid_desc ? grid_desc->step[k] : 0.0f;
+    }
     p.n0 = n0; p.n1 = n1; p.n_origin = n_origin; p.n_extent = n_extent;
     p.Wp = W + 2 * kBorder;
     p.nchunks = nchunks;
@@ -776,4 +802,31 @@ extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int 
         e = bf ? launch_lpb<8, false, false, true>(method, grid, smem, st, p) : launch_lpb<8, false, false, false>(method, grid, smem, st, p);
     if (e != cudaSuccess) return fail(MVHMR_ERR_CUDA, "unproject_kernel: %s", cudaGetErrorString(e));
     return check_launch("unproject_kernel");
+}
+
+extern "C" int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int feat_layout,
+                                         const float *proj, const float *coord, float *out,
+                                         int B, int V, int C, int H, int W,
+                                         int gx, int gy, int gz, int method,
+                                         int b0, int b1, long long n0, long long n1,
+                                         long long n_origin, long long n_extent,
+                                         unsigned tile_hint, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!coord && b0 < b1 && n0 < n1) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
+    static const mvhmr_grid_t none = {nullptr, nullptr, {0, 0, 0}, {0, 0, 0}};
+    return unproject_impl(feats, feat_dtype, feat_layout, proj, coord, coord ? nullptr : &none, out, B, V, C, H, W, gx, gy, gz, method,
+                          b0, b1, n0, n1, n_origin, n_extent, tile_hint, ws, ws_bytes, stream);
+}
+
+extern "C" int mvhmr_unproject_aggregate_grid(const void *feats, int feat_dtype, int feat_layout,
+                                              const float *proj, const mvhmr_grid_t *grid, float *out,
+                                              int B, int V, int C, int H, int W,
+                                              int gx, int gy, int gz, int method,
+                                              int b0, int b1, long long n0, long long n1,
+                                              long long n_origin, long long n_extent,
+                                              unsigned tile_hint, void *ws, size_t ws_bytes, void *stream)
+{
+    if (!grid) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_grid: null grid descriptor");
+    return unproject_impl(feats, feat_dtype, feat_layout, proj, nullptr, grid, out, B, V, C, H, W, gx, gy, gz, method,
+                          b0, b1, n0, n1, n_origin, n_extent, tile_hint, ws, ws_bytes, stream);
 }

@@ -42,8 +42,8 @@ def test_abi_version_and_sizes(built_lib):
     assert L.mvhmr_packed_bytes(_lib.F32, 1, 20, 7, 9) == 8 * 11 * 13 * 16
     assert L.mvhmr_packed_bytes(7, 2, 5, 7, 9) == 0
     assert L.mvhmr_unproject_workspace_bytes(_lib.F32, _lib.LAYOUT_PACKED, 8, 4, 32, 96, 96) == 0
-    assert L.mvhmr_soft_argmax3d_num_slices(64 ** 3) == 128
-    assert L.mvhmr_soft_argmax3d_workspace_bytes(8, 17, 64 ** 3) == 8 * 17 * 128 * 5 * 4
+    assert L.mvhmr_soft_argmax3d_num_slices(64 ** 3) == 512
+    assert L.mvhmr_soft_argmax3d_workspace_bytes(8, 17, 64 ** 3) == 8 * 17 * 512 * 5 * 4
 
 
 def test_argument_validation_needs_no_gpu(built_lib):

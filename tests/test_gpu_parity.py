@@ -213,6 +213,7 @@ def test_volume_generator_module(golden, case):
     vg.load_state_dict({"process_feature.0.weight": torch.from_numpy(z["conv_weight"]),
                         "process_feature.0.bias": torch.from_numpy(z["conv_bias"])})
     vg.train(bool(z["training"]))
+    vg.fuse_grid = False                             # two-step path first: exposes the coord volume
     torch.backends.cudnn.allow_tf32 = False          # the 1x1 conv is the reference's own torch op: keep it fp32
     torch.backends.cuda.matmul.allow_tf32 = False
     seen = {}
@@ -242,6 +243,12 @@ def test_volume_generator_module(golden, case):
     assert rel_l2(fused.cpu().numpy(), z["volumes"]) < OUR_TOL_SOFTMAX
     assert rel_l2(vol.cpu().numpy(), z["volumes"]) < SPEC_TOL_FP32
     assert vol.shape == z["volumes"].shape and vol.dtype == torch.float32
+    # default path: the grid is generated inside the fused kernel — same bits
+    vg.fuse_grid = True
+    np.random.seed(int(z["np_seed"]))
+    with torch.no_grad():
+        vol_fused = vg(*cuda(z["features"], z["proj_in"]), batch)
+    assert torch.equal(vol_fused, vol)
 
 
 def test_geometry_kernels_are_bit_exact(golden):
@@ -334,3 +341,51 @@ def test_deviation_from_the_torch_cuda_path_is_reported():
     print("torch-CUDA path vs ours %.3g | torch-CUDA vs fp64 %.3g | ours vs fp64 %.3g"
           % (gap, rel_l2(theirs, truth), rel_l2(ours, truth)))
     assert gap < 5e-5
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_backward_matches_torch_autograd(method):
+    """Gradient w.r.t. the features vs autograd through the reference's torch ops (CPU)."""
+    w = syn.Workload("t", B=2, V=3, C=5, H=14, W=18, G=9)
+    f, P, cv, _ = syn.make_inputs(w, seed=12, theta=0.4, behind_views=(2,))
+    g = torch.Generator().manual_seed(3)
+    gout = torch.randn(2, 5, 9, 9, 9, generator=g)
+    fr = f.clone().requires_grad_(True)
+    torch_port.unprojection(fr, P, cv, method).backward(gout)
+    fd, Pd, cvd, gd = cuda(f, P, cv, gout)
+    fd.requires_grad_(True)
+    out = agg.unprojection(fd, Pd, cvd, method)
+    assert out.requires_grad
+    out.backward(gd)
+    assert fd.grad.shape == f.shape and fd.grad.dtype == torch.float32
+    assert rel_l2(fd.grad.cpu().numpy(), fr.grad.numpy()) < 1e-5
+    if method in ("sum", "mean"):      # views behind the camera receive no gradient
+        assert float(fd.grad[:, 2].abs().max()) < float(fd.grad[:, 0].abs().max())
+
+
+def test_backward_bf16_features_and_module_training_step():
+    w = syn.Workload("t", B=1, V=4, C=8, H=16, W=16, G=8)
+    f, P, cv, _ = syn.make_inputs(w, seed=13)
+    fb = f.bfloat16()
+    fr = fb.float().clone().requires_grad_(True)
+    torch_port.unprojection(fr, P, cv, "softmax").sum().backward()
+    fd, Pd, cvd = cuda(fb, P, cv)
+    fd.requires_grad_(True)
+    agg.unprojection(fd, Pd, cvd, "softmax").sum().backward()
+    assert fd.grad.dtype == torch.bfloat16
+    assert rel_l2(fd.grad.float().cpu().numpy(), fr.grad.numpy()) < 1e-2
+    # a training step through the module: gradients reach the 1x1 conv
+    B, V, Cin, G = 2, 3, 6, 6
+    rng = np.random.default_rng(0)
+    cams = [[multiview.Camera(np.eye(3), [0.0, 0.0, 4000.0 + 100 * v], [[300.0, 0, 32], [0, 300.0, 32], [0, 0, 1]])
+             for _ in range(B)] for v in range(V)]
+    batch = {"images": np.zeros((B, V, 64, 64, 3), np.float32), "cameras": cams,
+             "keypoints_3d": [rng.normal(size=(17, 3)) * 50 for _ in range(B)]}
+    vg = agg.VolumeGenerator(volume_size=G, input_channels=Cin, output_channels=4, cuboid_side=2000.0, device=DEV)
+    vg.train()
+    np.random.seed(5)
+    feats = torch.randn(B, V, Cin, 16, 16, device=DEV)
+    vol = vg(feats, torch.zeros(B, V, 3, 4, device=DEV), batch)
+    vol.square().mean().backward()
+    gw = vg.process_feature[0].weight.grad
+    assert gw is not None and bool(torch.isfinite(gw).all()) and float(gw.abs().sum()) > 0
