@@ -31,6 +31,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from multiviewhmr_b200 import synthetic as syn  # noqa: E402
@@ -234,26 +235,55 @@ def main():
     # ---- end to end: pinned host inputs -> public API -> metric back on the host ------
     e2e_steps = max(5, min(args.steps, 30))
     metric_host = torch.empty((w.B, w.C, 3), dtype=torch.float32).pin_memory()
-    h2d = sum(t.numel() * t.element_size() for t in host_sets[0])
     d2h = metric_host.numel() * 4
+    # Host inputs of a step, as in VolumeGenerator.forward (models/aggregation.py:119-193): feature maps,
+    # projection matrices and the per-sample cuboid centre / rotation; the coordinate volume itself is
+    # built on the device (the reference builds it there too, :150-187).
+    rots_np = np.stack([np.eye(3, dtype=np.float32)] * w.B)
+    centers_sets = [syn.make_inputs(syn.Workload("c", w.B, 1, 1, 1, 1, 2), seed=1234 + 97 * rank + i)[3].numpy()
+                    for i in range(n_sets)]
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0][:2]) + w.B * 12 * 4
 
-    def e2e_step(i):
-        hf, hP, hcv = host_sets[i % n_sets]
-        f = hf.to(dev, non_blocking=True)
-        P = hP.to(dev, non_blocking=True)
-        cv = hcv.to(dev, non_blocking=True)
-        vol = agg.unprojection(f, P, cv, w.method, out=outs[i % 2])      # pack + fused kernel
-        joints = agg.soft_argmax_3d(vol, cv)                             # the step's metric: (B,C,3) expectations
-        metric_host.copy_(joints, non_blocking=True)
+    # Double-buffered: the host->device copies of step i+1 run on a copy stream while step i
+    # computes; every copy and every kernel of all e2e steps is inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    dev_in = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0][:2]) for _ in range(2)]
+    grid_in = [None, None]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
 
-    for i in range(3):
-        e2e_step(i)
+    def stage(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])            # the slot's previous user is done
+            for d, h in zip(dev_in[slot], host_sets[i % n_sets][:2]):
+                d.copy_(h, non_blocking=True)
+            grid_in[slot] = agg.build_coord_volumes(centers_sets[i % n_sets], rots_np, w.G, w.cuboid_side, dev)
+            copied[slot].record(copy_stream)
+
+    def e2e_run(n):
+        for ev in consumed:
+            ev.record(stream)
+        stage(0)
+        for i in range(n):
+            slot = i % 2
+            if i + 1 < n:
+                stage(i + 1)
+            stream.wait_event(copied[slot])
+            f, P = dev_in[slot]
+            cv = grid_in[slot]
+            cv.record_stream(stream)
+            vol = agg.unprojection(f, P, cv, w.method, out=outs[slot])   # pack + fused kernel
+            joints = agg.soft_argmax_3d(vol, cv)                         # the step's metric: (B,C,3) expectations
+            metric_host.copy_(joints, non_blocking=True)
+            consumed[slot].record(stream)
+
+    e2e_run(3)
     barrier()
     e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with sampler:
         e_start.record(stream)
-        for i in range(e2e_steps):
-            e2e_step(i)
+        e2e_run(e2e_steps)
         e_end.record(stream)
         barrier()
     e2e_ms = e_start.elapsed_time(e_end)
@@ -283,7 +313,7 @@ def main():
                          "step_frac": (alg / (ms_per_step * 1e-3) / 1e9) / peak},
             "e2e": {"value": units / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "path": "pinned host -> unprojection() -> soft_argmax_3d() -> host"},
+                    "path": "pinned host features+proj+centres -> (copy stream, double-buffered) build_coord_volumes() -> unprojection() -> soft_argmax_3d() -> host"},
             "gpu_launches": launches * world,
             "clocks": sampler.summary(),
         }

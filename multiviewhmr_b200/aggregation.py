@@ -159,7 +159,13 @@ def _grid_buffer(centers, rotations, device):
     """One H2D copy: B centres (B,3) followed by B rotations (B,9), fp32."""
     centers = np.ascontiguousarray(centers, dtype=np.float32).reshape(-1)
     rotations = np.ascontiguousarray(rotations, dtype=np.float32).reshape(-1)
-    return torch.from_numpy(np.concatenate([centers, rotations])).to(device)
+    return _to_device_async(np.concatenate([centers, rotations]), device)
+
+
+def _to_device_async(array, device):
+    """Small host array -> device through pinned staging, without blocking the host
+    (a pageable copy would wait for everything queued on the stream before it)."""
+    return torch.from_numpy(np.ascontiguousarray(array)).pin_memory().to(device, non_blocking=True)
 
 
 def soft_argmax_3d(volumes, coord_volumes):
@@ -242,8 +248,7 @@ def build_coord_volumes(centers, rotations, volume_size, cuboid_side, device):
     # cast to fp32 by torch when they meet the fp32 grid (`:156-158`)
     pos = np.float32(0.0 - cuboid_side / 2)
     step = np.float32(cuboid_side / (G - 1))
-    host = torch.from_numpy(np.concatenate([centers.reshape(B, 3), rotations.reshape(B, 9)], axis=1))
-    dev_buf = host.to(device)
+    dev_buf = _to_device_async(np.concatenate([centers.reshape(B, 3), rotations.reshape(B, 9)], axis=1), device)
     out = torch.empty((B, G, G, G, 3), dtype=torch.float32, device=device)
     cen, rot = dev_buf[:, :3].contiguous(), dev_buf[:, 3:].contiguous()
     with torch.cuda.device(device):
@@ -302,7 +307,7 @@ class VolumeGenerator(nn.Module):
             raise ValueError("VolumeGenerator.kind must be 'coco' or 'mpii', got %r" % (self.kind,))
         axis = _AXES[self.kind]
 
-        proj = torch.from_numpy(self._projections(batch, images_shape, features_shape, n_views, batch_size)).to(device)
+        proj = _to_device_async(self._projections(batch, images_shape, features_shape, n_views, batch_size), device)
 
         centers = np.empty((batch_size, 3), dtype=np.float32)
         rots = np.empty((batch_size, 3, 3), dtype=np.float32)
