@@ -27,6 +27,7 @@
 //     warp writes full 128-byte lines of the (B,C,N) output; every output value
 //     is written exactly once and no per-view volume exists anywhere.
 #include <cuda_bf16.h>
+#include <cstdlib>
 #include "mvhmr_common.cuh"
 
 namespace mvhmr {
@@ -69,7 +70,8 @@ struct UnprojParams {
     int gx, gy, gz;
     int x_lo, nx;          // x planes touched by [n0,n1)
     int lz, nseg;          // z segment length (<= kLzMax) and segments per z row
-    unsigned ntasks, nxb;  // warp tasks; x planes per row rounded up to a multiple of kWarps
+    unsigned ntasks, nxb;  // CTA tasks; x blocks (of kWarps planes) per row
+    unsigned ychunk;       // consecutive y rows a CTA sweeps before jumping
     int warp_smem;         // bytes of shared memory per warp
     int rec_bytes;         // bytes of one voxel record: V x float4 weights, then VP x int offsets
     int off_tile;          // byte offset of the output tile inside a warp's smem
@@ -81,98 +83,6 @@ struct ViewCell {
     int off;               // pixel offset of the nw corner inside a padded plane
     float w00, w01, w10, w11;
 };
-
-// a0/b, a1/b correctly rounded, sharing the reciprocal.  Same instruction
-// sequence as the div.rn.f32 fast path (MUFU.RCP, one Newton step, quotient,
-// exact remainder, correction); operands outside the safe exponent range
-// (including exact zeros) take the library division.
-__device__ __forceinline__ void div2_rn(float a0, float a1, float b, float &q0, float &q1)
-{
-    const float lo = fminf(fminf(fabsf(a0), fabsf(a1)), fabsf(b));
-    const float hi = fmaxf(fmaxf(fabsf(a0), fabsf(a1)), fabsf(b));
-    if (lo > 1e-30f && hi < 1e30f) {
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-        const float e = __fmaf_rn(-b, r, 1.0f);
-        r = __fmaf_rn(r, e, r);
-        const float t0 = __fmul_rn(a0, r), t1 = __fmul_rn(a1, r);
-        const float m0 = __fmaf_rn(-b, t0, a0), m1 = __fmaf_rn(-b, t1, a1);
-        q0 = __fmaf_rn(r, m0, t0);
-        q1 = __fmaf_rn(r, m1, t1);
-    } else {
-        q0 = __fdiv_rn(a0, b);
-        q1 = __fdiv_rn(a1, b);
-    }
-}
-
-// x / dx and y / dy for launch constants with rd = RN(1/d): q = x*rd, r = x - d*q
-// (exact), q' = q + r*rd is the correctly rounded quotient (Markstein) for
-// operands in the safe range; checked exhaustively for the usual map sizes in
-// the tests.
-__device__ __forceinline__ void div_const2(float x, float y, float dx, float rdx, float dy, float rdy,
-                                           float &qx, float &qy)
-{
-    const float lo = fminf(fabsf(x), fabsf(y)), hi = fmaxf(fabsf(x), fabsf(y));
-    if (lo > 1e-30f && hi < 1e30f) {
-        const float a = __fmul_rn(x, rdx), c = __fmul_rn(y, rdy);
-        qx = __fmaf_rn(__fmaf_rn(-dx, a, x), rdx, a);
-        qy = __fmaf_rn(__fmaf_rn(-dy, c, y), rdy, c);
-    } else {
-        qx = __fdiv_rn(x, dx);
-        qy = __fdiv_rn(y, dy);
-    }
-}
-
-// floor of a coordinate already clamped to a small range, without the XU pipe
-__device__ __forceinline__ float floor_small(float xc, int &xi)
-{
-    const float t = __fadd_rn(xc, kMagic);
-    float r = __fsub_rn(t, kMagic);               // rint(xc)
-    xi = __float_as_int(t) - 0x4B400000;
-    if (r > xc) { r = __fsub_rn(r, 1.0f); xi -= 1; }
-    return r;
-}
-
-// models/aggregation.py:38-51 + ATen grid_sampler unnormalize/compute_interp_params
-__device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1, const float4 &P2,
-                                              float X, float Y, float Z, const UnprojParams &p)
-{
-    const float xw = proj_row(X, Y, Z, P0.x, P0.y, P0.z, P0.w);
-    const float yw = proj_row(X, Y, Z, P1.x, P1.y, P1.z, P1.w);
-    const float ww = proj_row(X, Y, Z, P2.x, P2.y, P2.z, P2.w);
-    const bool invalid = ww <= 0.0f;                 // :42 depth must be > 0
-    const float wd = (ww == 0.0f) ? 1.0f : ww;       // :44 not to divide by zero
-    float x, y;
-    div2_rn(xw, yw, wd, x, y);
-    // :49-50  2*(x/feature_shape[0] - 0.5): x by H, y by W (reference behaviour)
-    float qx, qy;
-    div_const2(x, y, p.Hf, p.rH, p.Wf, p.rW, qx, qy);
-    const float gx = __fmul_rn(2.0f, __fsub_rn(qx, 0.5f));
-    const float gy = __fmul_rn(2.0f, __fsub_rn(qy, 0.5f));
-    // align_corners=True: (g + 1) * ((size - 1) / 2)
-    const float ix = __fmul_rn(__fadd_rn(gx, 1.0f), p.sx);
-    const float iy = __fmul_rn(__fadd_rn(gy, 1.0f), p.sy);
-    // Cell index from the position clamped into the zero border (NaN -> border).
-    // Inside the map clamped == unclamped, so floor and weights are the
-    // reference's; outside, every corner is a zero texel and only finiteness of
-    // the weights matters (0 * NaN = NaN, as in the reference).
-    const float ixc = fminf(fmaxf(ix, -2.0f), p.Wf), iyc = fminf(fmaxf(iy, -2.0f), p.Hf);
-    int x0, y0;
-    const float xf = floor_small(ixc, x0), yf = floor_small(iyc, y0);
-    float fw = __fsub_rn(ixc, xf), fn = __fsub_rn(iyc, yf);
-    if (!(fabsf(ix) < INFINITY)) fw = __int_as_float(0x7fc00000);
-    if (!(fabsf(iy) < INFINITY)) fn = __int_as_float(0x7fc00000);
-    const float fe = __fsub_rn(1.0f, fw), fs = __fsub_rn(1.0f, fn);
-    ViewCell c;
-    c.w00 = __fmul_rn(fs, fe); c.w01 = __fmul_rn(fs, fw);
-    c.w10 = __fmul_rn(fn, fe); c.w11 = __fmul_rn(fn, fw);
-    c.off = (y0 + kBorder) * p.Wp + (x0 + kBorder);
-    if (invalid) {                                   // :62 zero out non-valid points
-        c.off = 0;                                   // four border texels: exact +0
-        c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
-    }
-    return c;
-}
 
 // ---- packed f32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) ---------------
 typedef unsigned long long u64;
@@ -207,6 +117,92 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b)
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// The x and y pipelines of the projection are identical chains of IEEE operations, so they
+// run as one packed f32x2 stream (each half is a correctly rounded fp32 op; results are
+// bit-identical to the scalar sequence).
+
+// (a.x/b, a.y/b) correctly rounded.  Same instruction sequence as the div.rn.f32 fast path
+// (MUFU.RCP, one Newton step, quotient, exact remainder, correction); operands outside the
+// safe exponent range (including exact zeros) take the library division.
+__device__ __forceinline__ u64 div2_rn(u64 a, float b)
+{
+    const f2 av = upk(a);
+    const float lo = fminf(fminf(fabsf(av.x), fabsf(av.y)), fabsf(b));
+    const float hi = fmaxf(fmaxf(fabsf(av.x), fabsf(av.y)), fabsf(b));
+    if (lo > 1e-30f && hi < 1e30f) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+        const float e = __fmaf_rn(-b, r, 1.0f);
+        r = __fmaf_rn(r, e, r);
+        const u64 rr = pk(r, r), nb = pk(-b, -b);
+        const u64 t = mul2(a, rr);
+        const u64 m = fma2(nb, t, a);
+        return fma2(rr, m, t);
+    }
+    return pk(__fdiv_rn(av.x, b), __fdiv_rn(av.y, b));
+}
+
+// (x/dx, y/dy) for launch constants with rd = RN(1/d): q = x*rd, r = x - d*q (exact),
+// q' = q + r*rd is the correctly rounded quotient (Markstein) for operands in the safe
+// range; checked exhaustively for the usual map sizes in the tests.
+__device__ __forceinline__ u64 div_const2(u64 xy, u64 nd /*(-dx,-dy)*/, u64 rd /*(1/dx,1/dy)*/, float dx, float dy)
+{
+    const f2 v = upk(xy);
+    const float lo = fminf(fabsf(v.x), fabsf(v.y)), hi = fmaxf(fabsf(v.x), fabsf(v.y));
+    if (lo > 1e-30f && hi < 1e30f) {
+        const u64 q = mul2(xy, rd);
+        return fma2(fma2(nd, q, xy), rd, q);
+    }
+    return pk(__fdiv_rn(v.x, dx), __fdiv_rn(v.y, dy));
+}
+
+// models/aggregation.py:38-51 + ATen grid_sampler unnormalize/compute_interp_params
+__device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1, const float4 &P2,
+                                              float X, float Y, float Z, const UnprojParams &p)
+{
+    // [X Y Z 1] . P rows 0,1 (packed) and row 2: mul, fma, fma, add in k order
+    u64 hw = mul2(pk(X, X), pk(P0.x, P1.x));
+    hw = fma2(pk(Y, Y), pk(P0.y, P1.y), hw);
+    hw = fma2(pk(Z, Z), pk(P0.z, P1.z), hw);
+    hw = add2(hw, pk(P0.w, P1.w));
+    const float ww = proj_row(X, Y, Z, P2.x, P2.y, P2.z, P2.w);
+    const bool invalid = ww <= 0.0f;                 // :42 depth must be > 0
+    const float wd = (ww == 0.0f) ? 1.0f : ww;       // :44 not to divide by zero
+    const u64 xy = div2_rn(hw, wd);
+    // :49-50  2*(x/feature_shape[0] - 0.5): x by H, y by W (reference behaviour)
+    const u64 q = div_const2(xy, pk(-p.Hf, -p.Wf), pk(p.rH, p.rW), p.Hf, p.Wf);
+    const u64 g = mul2(pk(2.0f, 2.0f), add2(q, pk(-0.5f, -0.5f)));
+    // align_corners=True: (g + 1) * ((size - 1) / 2)
+    const f2 i = upk(mul2(add2(g, pk(1.0f, 1.0f)), pk(p.sx, p.sy)));
+    // Cell index from the position clamped into the zero border (NaN -> border).
+    // Inside the map clamped == unclamped, so floor and weights are the
+    // reference's; outside, every corner is a zero texel and only finiteness of
+    // the weights matters (0 * NaN = NaN, as in the reference).
+    const float ixc = fminf(fmaxf(i.x, -2.0f), p.Wf), iyc = fminf(fmaxf(i.y, -2.0f), p.Hf);
+    const u64 c2 = pk(ixc, iyc);
+    const u64 t2 = add2(c2, pk(kMagic, kMagic));                 // rounds to integer
+    f2 r = upk(add2(t2, pk(-kMagic, -kMagic)));                  // rint
+    const f2 tb = upk(t2);
+    int x0 = __float_as_int(tb.x) - 0x4B400000, y0 = __float_as_int(tb.y) - 0x4B400000;
+    if (r.x > ixc) { r.x = __fsub_rn(r.x, 1.0f); x0 -= 1; }      // rint -> floor
+    if (r.y > iyc) { r.y = __fsub_rn(r.y, 1.0f); y0 -= 1; }
+    f2 fr = upk(add2(c2, pk(-r.x, -r.y)));                       // (w, n) = pos - floor(pos)
+    if (!(fabsf(i.x) < INFINITY)) fr.x = __int_as_float(0x7fc00000);
+    if (!(fabsf(i.y) < INFINITY)) fr.y = __int_as_float(0x7fc00000);
+    const f2 one_m = upk(add2(pk(1.0f, 1.0f), pk(-fr.x, -fr.y)));   // (e, s) = 1 - (w, n)
+    const u64 ew = pk(one_m.x, fr.x);                            // (e, w)
+    const f2 top = upk(mul2(pk(one_m.y, one_m.y), ew));          // s*e, s*w
+    const f2 bot = upk(mul2(pk(fr.y, fr.y), ew));                // n*e, n*w
+    ViewCell c;
+    c.w00 = top.x; c.w01 = top.y; c.w10 = bot.x; c.w11 = bot.y;
+    c.off = (y0 + kBorder) * p.Wp + (x0 + kBorder);
+    if (invalid) {                                   // :62 zero out non-valid points
+        c.off = 0;                                   // four border texels: exact +0
+        c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
+    }
+    return c;
+}
+
 __device__ __forceinline__ float ex2_approx(float x)   // bare MUFU.EX2; arguments here are <= 0
 {
     float r;
@@ -316,9 +312,7 @@ struct Fuse2 {
     {
         if (METHOD == MVHMR_SUM) return upk(a);
         if (METHOD == MVHMR_MEAN) {                    // x / V, correctly rounded (see div_const2)
-            f2 r = upk(a), q;
-            div_const2(r.x, r.y, Vf, 1.0f / Vf, Vf, 1.0f / Vf, q.x, q.y);
-            return q;
+            return upk(div_const2(a, pk(-Vf, -Vf), pk(1.0f / Vf, 1.0f / Vf), Vf, Vf));
         }
         if (METHOD == MVHMR_MAX) { f2 r; r.x = m0; r.y = m1; return r; }
         const f2 s = upk(S);
@@ -360,17 +354,24 @@ unproject_kernel(const UnprojParams p)
     const int wbytes = EXACT ? VMAX * 16 : p.V * 16;
     const int rec_bytes = EXACT ? VMAX * 16 + ((VMAX + 3) & ~3) * 4 : p.rec_bytes;
 
-    // Persistent CTAs: tasks are numbered x-fastest and dealt out in rounds of gridDim.x * kWarps,
-    // so the warps of a CTA always work on consecutive x planes of one (sample, z segment, y) row
-    // while drifting apart in phase (projection / gathers / stores overlap across warps).
-    for (unsigned task = blockIdx.x * kWarps + warp; task < p.ntasks; task += gridDim.x * kWarps) {
-    unsigned t = task / p.nxb;                       // task -> (b, z segment, y, x block, x in block)
-    const unsigned xblk = task - t * p.nxb;
-    const int vy = (int)(t % (unsigned)p.gy); t /= (unsigned)p.gy;
+    // Persistent CTAs.  A CTA task = kWarps consecutive x planes of one (sample, z segment, y)
+    // row, one plane per warp: their projections overlap almost completely in every view, so the
+    // CTA's texel footprint stays L1-resident.  Warps are never synchronised with each other and
+    // drift apart in phase (projection / gathers / stores of different warps overlap).
+    // Tasks are dealt in chunks of p.ychunk consecutive y rows, chunk k to CTA k % gridDim.x:
+    // all CTAs work on neighbouring chunks (one sample's maps stay in L2) and a CTA's
+    // consecutive tasks share texel rows in L1.
+    const unsigned nchunk = (p.ntasks + p.ychunk - 1) / p.ychunk;
+    for (unsigned ck = blockIdx.x; ck < nchunk; ck += gridDim.x)
+    for (unsigned ct = ck * p.ychunk; ct < min(p.ntasks, (ck + 1) * p.ychunk); ++ct) {
+    unsigned t = ct / (unsigned)p.gy;                // task -> (b, z segment, x block, y)
+    const int vy = (int)(ct - t * (unsigned)p.gy);
+    const unsigned xb = t % p.nxb; t /= p.nxb;
     const int seg = (int)(t % (unsigned)p.nseg);
     const int b = p.b0 + (int)(t / (unsigned)p.nseg);
-    if ((int)xblk >= p.nx) continue;                 // padding of the last x block
-    const int vx = p.x_lo + (int)xblk;
+    const int xi = (int)xb * kWarps + warp;
+    if (xi >= p.nx) continue;                        // padding of the last x block
+    const int vx = p.x_lo + xi;
     const int z0 = seg * p.lz;
     const int zn = min(p.lz, p.gz - z0);             // voxels in this segment (<= 32)
     const int steps = (zn + ngroups - 1) >> (5 - lpv_log);
@@ -400,11 +401,17 @@ unproject_kernel(const UnprojParams p)
         }
         unsigned char *rec = recs + lane * rec_bytes + (lane / steps) * 16;
         const float4 *Pb = reinterpret_cast<const float4 *>(p.proj + (size_t)b * p.V * 12);
-        for (int v = 0; v < p.V; ++v) {
+        auto one_view = [&](int v) {
             const float4 P0 = __ldg(Pb + 3 * v), P1 = __ldg(Pb + 3 * v + 1), P2 = __ldg(Pb + 3 * v + 2);
             const ViewCell c = make_cell(P0, P1, P2, X, Y, Z, p);
             reinterpret_cast<float4 *>(rec)[v] = make_float4(c.w00, c.w01, c.w10, c.w11);
             reinterpret_cast<int *>(rec + wbytes)[v] = mine ? c.off : -1;
+        };
+        if (EXACT) {                                 // independent chains of all views interleave
+#pragma unroll
+            for (int v = 0; v < VMAX; ++v) one_view(v);
+        } else {
+            for (int v = 0; v < p.V; ++v) one_view(v);
         }
     }
     __syncwarp();
@@ -781,16 +788,20 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
     p.rH = 1.0f / (float)H; p.rW = 1.0f / (float)W;
-    p.nxb = (unsigned)((p.nx + kWarps - 1) / kWarps * kWarps);
+    p.nxb = (unsigned)((p.nx + kWarps - 1) / kWarps);
     const long long ntasks = (long long)p.nb * p.nseg * gy * p.nxb;
     if (ntasks > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: too many z rows in one call");
     p.ntasks = (unsigned)ntasks;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const unsigned ctas = (unsigned)((ntasks + kWarps - 1) / kWarps);
     const unsigned resident = (unsigned)sms * MVHMR_MINBLOCKS;       // one CTA (or MINBLOCKS) per SM, persistent
-    const dim3 grid(ctas < resident ? ctas : resident);
+    p.ychunk = 1;                                                    // largest y sweep that still leaves >= 6 rounds
+    for (unsigned yc = 8; yc > 1; yc >>= 1)
+        if ((unsigned)gy % yc == 0 && ntasks / yc >= 6ll * resident) { p.ychunk = yc; break; }
+    if (const char *env = getenv("MVHMR_YCHUNK")) { const int v = atoi(env); if (v >= 1) p.ychunk = (unsigned)v; }   // tuning knob
+    const unsigned nchunk = (unsigned)((ntasks + p.ychunk - 1) / p.ychunk);
+    const dim3 grid(nchunk < resident ? nchunk : resident);
     cudaError_t e;
     if (V == 4)
         e = bf ? launch_lpb<4, true, MVHMR_CACHE4, true>(method, grid, smem, st, p) : launch_lpb<4, true, MVHMR_CACHE4, false>(method, grid, smem, st, p);
