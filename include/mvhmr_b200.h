@@ -165,6 +165,12 @@ int mvhmr_unproject_aggregate_backward(const float *grad_out, const void *feats,
                                        const float *proj, const float *coord, float *grad_feats,
                                        int B, int V, int C, int H, int W, long long N, int method, void *stream);
 
+/* Self-test: runs the kernel's two exact-division shortcuts (division by a launch
+ * constant via reciprocal + FMA correction; shared-reciprocal division) for ALL
+ * 2^32 numerators against div.rn.f32 with divisor d and ADDS the number of
+ * bitwise mismatches to *mismatches (device pointer, zeroed by the caller). */
+int mvhmr_selftest_division(float d, unsigned long long *mismatches, void *stream);
+
 /* ---- 3-D soft-argmax ------------------------------------------------------ */
 /* Not in the reference; upstream definition
  * (Learnable-Triangulation integrate_tensor_3d_with_coordinates, cited by URL at

@@ -606,6 +606,27 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
     }
 }
 
+// Self-test of the two exact-division shortcuts against div.rn.f32 over ALL 2^32 numerators.
+__global__ void __launch_bounds__(256)
+selftest_division_kernel(float d, unsigned long long *mismatches)
+{
+    const float rd = __fdiv_rn(1.0f, d);
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < (1ull << 32);
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)i);
+        const float ref = __fdiv_rn(x, d);
+        const f2 a = upk(div_const2(pk(x, x), pk(-d, -d), pk(rd, rd), d, d));      // division by a launch constant
+        const f2 b = upk(div2_rn(pk(x, -x), d));                                    // shared-reciprocal division
+        const float nref = __fdiv_rn(-x, d);
+        const bool ok = (__float_as_uint(a.x) == __float_as_uint(ref) || (a.x != a.x && ref != ref)) &&
+                        (__float_as_uint(b.x) == __float_as_uint(ref) || (b.x != b.x && ref != ref)) &&
+                        (__float_as_uint(b.y) == __float_as_uint(nref) || (b.y != b.y && nref != nref));
+        bad += ok ? 0 : 1;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 static int pow2ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
 static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; }
 
@@ -840,4 +861,11 @@ extern "C" int mvhmr_unproject_aggregate_grid(const void *feats, int feat_dtype,
     if (!grid) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_grid: null grid descriptor");
     return unproject_impl(feats, feat_dtype, feat_layout, proj, nullptr, grid, out, B, V, C, H, W, gx, gy, gz, method,
                           b0, b1, n0, n1, n_origin, n_extent, tile_hint, ws, ws_bytes, stream);
+}
+
+extern "C" int mvhmr_selftest_division(float d, unsigned long long *mismatches, void *stream)
+{
+    if (!mismatches) return fail(MVHMR_ERR_INVALID_ARGUMENT, "selftest_division: null pointer");
+    selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d, mismatches);
+    return check_launch("selftest_division_kernel");
 }

@@ -389,3 +389,12 @@ def test_backward_bf16_features_and_module_training_step():
     vol.square().mean().backward()
     gw = vg.process_feature[0].weight.grad
     assert gw is not None and bool(torch.isfinite(gw).all()) and float(gw.abs().sum()) > 0
+
+
+@pytest.mark.parametrize("d", [7.0, 10.0, 12.0, 14.0, 16.0, 24.0, 56.0, 64.0, 96.0, 100.0, 128.0, 224.0, 3.0, 4.0, 8.0, 4503.7])
+def test_exact_division_shortcuts_exhaustively(d):
+    """The kernel divides by H / W / V with reciprocal + FMA correction and shares one reciprocal
+    between x/w and y/w.  Both must equal IEEE division bit for bit: checked for all 2^32 numerators."""
+    bad = torch.zeros(1, dtype=torch.int64, device=DEV)
+    _lib.check(_lib.load().mvhmr_selftest_division(d, _lib.ptr(bad), _lib.stream_ptr(torch.device(DEV))))
+    assert int(bad.item()) == 0
