@@ -93,7 +93,9 @@ def test_cfg3_bf16_and_soft_argmax():
 @pytest.mark.parametrize("B,V,C,H,W,G", [
     (1, 1, 1, 5, 7, (3, 4, 5)), (2, 2, 3, 9, 6, (4, 4, 4)), (1, 3, 5, 16, 12, (2, 9, 33)),
     (1, 4, 13, 8, 8, (7, 3, 16)), (2, 5, 8, 12, 20, (5, 5, 40)), (1, 8, 64, 10, 10, (3, 3, 32)),
-    (1, 9, 4, 10, 10, (2, 2, 16)), (1, 17, 12, 10, 10, (2, 3, 8)), (3, 4, 32, 24, 24, (16, 16, 16))])
+    (1, 9, 4, 10, 10, (2, 2, 16)), (1, 17, 12, 10, 10, (2, 3, 8)), (3, 4, 32, 24, 24, (16, 16, 16)),
+    # the reference's real operating point (cfg/baseline.yaml): 256 channels, 7x7 maps, 16^3 grid
+    (2, 4, 256, 7, 7, (16, 16, 16)), (1, 3, 200, 6, 5, (4, 4, 20)), (1, 2, 32, 16, 16, (3, 2, 80))])
 @pytest.mark.parametrize("method", METHODS)
 def test_ragged_shapes(B, V, C, H, W, G, method):
     g = torch.Generator().manual_seed(B * 1000 + V * 100 + C)
