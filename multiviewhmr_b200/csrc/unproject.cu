@@ -419,9 +419,6 @@ unproject_kernel(const UnprojParams p)
     const bool single = EXACT || p.V <= VMAX;        // all views fit one register block
     for (int cb = 0; cb < p.nchunks; cb += kVecPass) {           // channel passes (C > 128 fp32 / 256 bf16)
         const char *lane_base = p.packed + (size_t)b * p.V * p.plane_bytes + ((size_t)(cb + chunk) << 4);
-        const char *vbase[VMAX];
-#pragma unroll
-        for (int v = 0; v < VMAX; ++v) vbase[v] = lane_base + (size_t)v * p.plane_bytes;
 #ifndef MVHMR_TV
 #define MVHMR_TV 4
 #endif
@@ -447,8 +444,8 @@ unproject_kernel(const UnprojParams p)
                 if (EXACT || v < nv) {
                     const int o = max(off[v], 0);
                     if (!CACHE || o != cur[v]) {
-                        const char *q0 = (single ? vbase[(v0 + v) % VMAX] : lane_base + (size_t)(v0 + v) * p.plane_bytes)
-                                         + ((unsigned)o << lpb);
+                        // view plane offset is warp-uniform; only the cell offset is per lane
+                        const char *q0 = lane_base + ((size_t)(v0 + v) * p.plane_bytes + ((size_t)(unsigned)o << lpb));
                         const char *q1 = q0 + row;
                         tex[v][0] = __ldg(reinterpret_cast<const uint4 *>(q0));
                         tex[v][1] = __ldg(reinterpret_cast<const uint4 *>(q0 + px));
