@@ -554,8 +554,9 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
     constexpr int CPT = BF16 ? 8 : 4;            // channels per 16-byte vector
     constexpr int CB = 64;                       // channels per tile
     constexpr int XB = 128;                      // pixels per tile
-    __shared__ float tile_f[BF16 ? 1 : CB * (XB + 1)];
-    __shared__ unsigned short tile_h[BF16 ? CB * (XB + 2) : 1];
+    extern __shared__ __align__(16) unsigned char pack_smem[];    // min(CP, CB) channel rows of the tile
+    float *tile_f = reinterpret_cast<float *>(pack_smem);
+    unsigned short *tile_h = reinterpret_cast<unsigned short *>(pack_smem);
     const int bv = blockIdx.x / Hp;
     const int y = blockIdx.x % Hp - kBorder;
     uint4 *dst_row = packed + (size_t)blockIdx.x * Wp * nchunks;
@@ -693,10 +694,12 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     const int nchunks = nchunks_of(feat_dtype, C), Hp = H + 2 * kBorder, Wp = W + 2 * kBorder;
     const long long rows = (long long)BV * Hp;
     if (rows > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: too many rows");
+    const int cp = nchunks * (feat_dtype == MVHMR_BF16 ? 8 : 4);
+    const int tile_rows = cp < 64 ? cp : 64;                       // CB in the kernel
     if (feat_dtype == MVHMR_BF16)
-        pack_kernel<true><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
+        pack_kernel<true><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 2) * 2, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
     else
-        pack_kernel<false><<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
+        pack_kernel<false><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 1) * 4, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
     return check_launch("pack_kernel");
 }
 
