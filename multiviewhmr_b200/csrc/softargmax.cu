@@ -2,23 +2,21 @@
 //   p = softmax(vol[b,j,:]);  out[b,j,:] = sum_n p[n] * coord[b,n,:]
 //
 // HBM-bound single pass: every volume value is read exactly once with 16-byte
-// streaming loads, every coordinate once per sample (not once per joint).  A CTA
-// stages the coordinates of 2048 voxels of one sample in shared memory; its work
-// items are (joint, 512-voxel quarter) pairs dealt round-robin to the 8 warps, so
-// a warp reduces a whole item alone: per lane 16 values -> online-softmax record
-// (max, sum e, sum e*x, sum e*y, sum e*z), ONE 5-step shuffle merge per item, no
-// block-level synchronisation after the staging.  A tiny second kernel merges the
-// per-quarter records — the same merge a slab-sharded multi-GPU run uses across
-// ranks.
+// streaming loads, every coordinate once per sample (not once per joint).  A warp owns
+// 512 voxels of one sample: it keeps their coordinates in registers (16 voxels per lane)
+// and walks a chunk of <= 8 joints, three joints' loads in flight; per joint the warp agrees on the
+// max first, so the partial sums (sum e, sum e*x, sum e*y, sum e*z) merge with plain
+// shuffle-adds, and writes one record per (b, joint, 512-voxel slice).  No shared memory,
+// no block-level synchronisation.  A tiny second kernel merges the per-slice records —
+// the same merge a slab-sharded multi-GPU run uses across ranks.
 #include "mvhmr_common.cuh"
 
 namespace mvhmr {
 
-constexpr int kSaBlock = 256;
+constexpr int kSaBlock = 128;
 constexpr int kSaWarps = kSaBlock / 32;
-constexpr int kSliceVox = 2048;                        // voxels staged per CTA
 constexpr int kItemVox = 512;                          // voxels of one record (one warp, 16 per lane)
-constexpr int kItemsPerSlice = kSliceVox / kItemVox;
+constexpr int kSaJointChunk = 8;                       // at most this many joints per warp (grid.z splits J)
 constexpr float kSaLog2e = 1.4426950408889634f;
 
 __device__ __forceinline__ float sa_ex2(float x)
@@ -56,41 +54,51 @@ __device__ __forceinline__ Rec shfl_xor(const Rec &r, int mask)
 
 // VEC: N % 4 == 0 and n0 % 4 == 0 -> 16-byte loads of vol
 template <bool VEC>
-__global__ void __launch_bounds__(kSaBlock, 3)
+__global__ void __launch_bounds__(kSaBlock)
 soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restrict__ coord,
-                            float *__restrict__ partials, int J, long long N, long long n0, long long n1, int S)
+                            float *__restrict__ partials, int J, int jchunk, long long N, long long n0, long long n1, int S)
 {
-    __shared__ __align__(16) float cs[kSliceVox * 3];          // xyz of the slice's voxels
-    const int b = blockIdx.y, slice = blockIdx.x;
+    const int b = blockIdx.y;
+    const int j0 = blockIdx.z * jchunk, j1 = min(J, j0 + jchunk);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long base = n0 + (long long)slice * kSliceVox;
-    const int nvox = (int)min((long long)kSliceVox, n1 - base);
+    const int slice = blockIdx.x * kSaWarps + warp;             // 512-voxel slice of this warp
+    if (slice >= S) return;
+    const long long base = n0 + (long long)slice * kItemVox;
+    const int qn = (int)min((long long)kItemVox, n1 - base);    // voxels in this slice
 
-    // stage the coordinates (contiguous nvox*3 floats)
+    // coordinates of this lane's 16 voxels (4 runs of 4 consecutive voxels), kept in registers
+    float cx[16], cy[16], cz[16];
     {
         const float *cp = coord + ((size_t)b * N + base) * 3;
-        const int nfl = nvox * 3;
-        if ((((uintptr_t)cp) & 15) == 0) {
-            for (int i = threadIdx.x * 4; i < nfl; i += kSaBlock * 4) {
-                if (i + 4 <= nfl) *reinterpret_cast<float4 *>(cs + i) = __ldg(reinterpret_cast<const float4 *>(cp + i));
-                else for (int k = i; k < nfl; ++k) cs[k] = __ldg(cp + k);
-            }
-        } else {
-            for (int i = threadIdx.x; i < nfl; i += kSaBlock) cs[i] = __ldg(cp + i);
-        }
-    }
-    __syncthreads();
-
-    const int nq = (nvox + kItemVox - 1) / kItemVox;             // quarters present in this slice
-    const int nitems = J * nq;
-
-    auto load_item = [&](int item, float *x) {
-        const int j = (nq == kItemsPerSlice) ? item / kItemsPerSlice : item / nq, q = item - j * nq;
-        const float *vp = vol + ((size_t)b * J + j) * N + base + q * kItemVox;
-        const int qn = min(kItemVox, nvox - q * kItemVox);       // voxels in this quarter
+        const bool al = (((uintptr_t)cp) & 15) == 0;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-            const int v0 = (h * 32 + lane) * 4;                  // this lane's 4 consecutive voxels
+            const int v0 = (h * 32 + lane) * 4;
+            if (al && v0 + 4 <= qn) {
+                const float4 a = __ldg(reinterpret_cast<const float4 *>(cp + v0 * 3));
+                const float4 d = __ldg(reinterpret_cast<const float4 *>(cp + v0 * 3) + 1);
+                const float4 e = __ldg(reinterpret_cast<const float4 *>(cp + v0 * 3) + 2);
+                cx[4 * h] = a.x; cy[4 * h] = a.y; cz[4 * h] = a.z;
+                cx[4 * h + 1] = a.w; cy[4 * h + 1] = d.x; cz[4 * h + 1] = d.y;
+                cx[4 * h + 2] = d.z; cy[4 * h + 2] = d.w; cz[4 * h + 2] = e.x;
+                cx[4 * h + 3] = e.y; cy[4 * h + 3] = e.z; cz[4 * h + 3] = e.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const bool in = v0 + i < qn;
+                    cx[4 * h + i] = in ? __ldg(cp + (v0 + i) * 3) : 0.0f;
+                    cy[4 * h + i] = in ? __ldg(cp + (v0 + i) * 3 + 1) : 0.0f;
+                    cz[4 * h + i] = in ? __ldg(cp + (v0 + i) * 3 + 2) : 0.0f;
+                }
+            }
+        }
+    }
+
+    auto load_joint = [&](int j, float *x) {
+        const float *vp = vol + ((size_t)b * J + j) * N + base;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int v0 = (h * 32 + lane) * 4;
             if (VEC && v0 + 4 <= qn) {
                 const float4 a = __ldcs(reinterpret_cast<const float4 *>(vp + v0));
                 x[4 * h] = a.x; x[4 * h + 1] = a.y; x[4 * h + 2] = a.z; x[4 * h + 3] = a.w;
@@ -100,42 +108,24 @@ soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restri
             }
         }
     };
-    auto reduce_item = [&](int item, const float *x) {
-        const int j = (nq == kItemsPerSlice) ? item / kItemsPerSlice : item / nq, q = item - j * nq;
-        const int qn = min(kItemVox, nvox - q * kItemVox);
-        const float *cq = cs + q * kItemVox * 3;
+    auto reduce_joint = [&](int j, const float *x) {
         Rec r;
         r.m = x[0];
 #pragma unroll
         for (int i = 1; i < 16; ++i) r.m = fmaxf(r.m, x[i]);
-        // the warp agrees on the item's max first, so the sums merge with plain adds
+        // the warp agrees on the slice's max first, so the sums merge with plain adds
 #pragma unroll
         for (int mask = 16; mask >= 1; mask >>= 1) r.m = fmaxf(r.m, __shfl_xor_sync(0xffffffffu, r.m, mask));
         const float ms = (r.m == -INFINITY) ? 0.0f : r.m;
         const float nm = -ms * kSaLog2e;
         r.S = r.X = r.Y = r.Z = 0.0f;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
-            const int v0 = (h * 32 + lane) * 4;
-            float c[12];
-            if (v0 + 4 <= qn) {
-                const float4 a = *reinterpret_cast<const float4 *>(cq + v0 * 3);
-                const float4 d = *reinterpret_cast<const float4 *>(cq + v0 * 3 + 4);
-                const float4 e = *reinterpret_cast<const float4 *>(cq + v0 * 3 + 8);
-                c[0] = a.x; c[1] = a.y; c[2] = a.z; c[3] = a.w; c[4] = d.x; c[5] = d.y;
-                c[6] = d.z; c[7] = d.w; c[8] = e.x; c[9] = e.y; c[10] = e.z; c[11] = e.w;
-            } else {
-#pragma unroll
-                for (int k = 0; k < 12; ++k) c[k] = (v0 * 3 + k < qn * 3) ? cq[v0 * 3 + k] : 0.0f;
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float e = sa_ex2(fmaf(x[4 * h + i], kSaLog2e, nm));
-                r.S += e;
-                r.X = fmaf(e, c[3 * i], r.X);
-                r.Y = fmaf(e, c[3 * i + 1], r.Y);
-                r.Z = fmaf(e, c[3 * i + 2], r.Z);
-            }
+        for (int i = 0; i < 16; ++i) {
+            const float e = sa_ex2(fmaf(x[i], kSaLog2e, nm));
+            r.S += e;
+            r.X = fmaf(e, cx[i], r.X);
+            r.Y = fmaf(e, cy[i], r.Y);
+            r.Z = fmaf(e, cz[i], r.Z);
         }
 #pragma unroll
         for (int mask = 16; mask >= 1; mask >>= 1) {
@@ -145,33 +135,25 @@ soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restri
             r.Z += __shfl_xor_sync(0xffffffffu, r.Z, mask);
         }
         if (lane == 0) {
-            float *o = partials + (((size_t)b * J + j) * S + (size_t)slice * kItemsPerSlice + q) * 5;
+            float *o = partials + (((size_t)b * J + j) * S + slice) * 5;
             o[0] = r.m; o[1] = r.S; o[2] = r.X; o[3] = r.Y; o[4] = r.Z;
         }
     };
 
-    // two items in flight per warp: the next item's 16-byte loads are issued before the current
-    // item's exp / sum chain
-    float xa[16], xb[16];
-    int item = warp;
-    if (item < nitems) load_item(item, xa);
-    while (item < nitems) {
-        const int nxt = item + kSaWarps;
-        if (nxt < nitems) load_item(nxt, xb);
-        reduce_item(item, xa);
-        if (nxt >= nitems) break;
-        const int nx2 = nxt + kSaWarps;
-        if (nx2 < nitems) load_item(nx2, xa);
-        reduce_item(nxt, xb);
-        item = nx2;
-    }
-    // quarters that do not exist in a ragged last slice still own a record slot: mark them empty
-    for (int item = threadIdx.x; item < J * (kItemsPerSlice - nq); item += kSaBlock) {
-        const int j = item / (kItemsPerSlice - nq), q = nq + item % (kItemsPerSlice - nq);
-        if ((size_t)slice * kItemsPerSlice + q < (size_t)S) {
-            float *o = partials + (((size_t)b * J + j) * S + (size_t)slice * kItemsPerSlice + q) * 5;
-            o[0] = -INFINITY; o[1] = 0.0f; o[2] = 0.0f; o[3] = 0.0f; o[4] = 0.0f;
-        }
+    // three joints' loads in flight per warp: joint j+2 is requested before joint j's
+    // exp / sum chain runs
+    float xa[16], xb[16], xc[16];
+    load_joint(j0, xa);
+    if (j0 + 1 < j1) load_joint(j0 + 1, xb);
+    for (int j = j0; j < j1; j += 3) {
+        if (j + 2 < j1) load_joint(j + 2, xc);
+        reduce_joint(j, xa);
+        if (j + 1 >= j1) break;
+        if (j + 3 < j1) load_joint(j + 3, xa);
+        reduce_joint(j + 1, xb);
+        if (j + 2 >= j1) break;
+        if (j + 4 < j1) load_joint(j + 4, xb);
+        reduce_joint(j + 2, xc);
     }
 }
 
@@ -232,12 +214,13 @@ extern "C" int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord
     if (B > 65535) return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: B=%d exceeds 65535", B);
     if (!vol || !coord || !partials) return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: null pointer");
     const int S = mvhmr_soft_argmax3d_num_slices(n1 - n0);
-    dim3 grid((unsigned)((n1 - n0 + kSliceVox - 1) / kSliceVox), B);
+    const int nz = (J + kSaJointChunk - 1) / kSaJointChunk, jchunk = (J + nz - 1) / nz;
+    dim3 grid((unsigned)((S + kSaWarps - 1) / kSaWarps), B, nz);
     const bool vec = (N % 4 == 0) && (n0 % 4 == 0) && (((uintptr_t)vol & 15) == 0);
     if (vec)
-        soft_argmax_partials_kernel<true><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, N, n0, n1, S);
+        soft_argmax_partials_kernel<true><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S);
     else
-        soft_argmax_partials_kernel<false><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, N, n0, n1, S);
+        soft_argmax_partials_kernel<false><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S);
     return check_launch("soft_argmax_partials_kernel");
 }
 
