@@ -46,6 +46,7 @@ constexpr int kBorder = 2;
 #define MVHMR_LZCAP 32
 #endif
 constexpr int kWarps = MVHMR_WARPS;       // warps per CTA: consecutive x planes share their texel footprint in L1
+constexpr unsigned kNotMine = 0xffffffffu;   // view-0 offset of a voxel outside the shard window (real offsets are multiples of 16)
 constexpr int kLzMax = 32;                // voxels of one warp task (z segment): one per lane in phase A
 constexpr int kYRows = 1;                 // consecutive y rows walked by one CTA
 constexpr int kVecPass = 32;              // 16-byte channel vectors handled per pass (at most one per lane)
@@ -72,6 +73,8 @@ struct UnprojParams {
     int lz, nseg;          // z segment length (<= kLzMax) and segments per z row
     unsigned ntasks, nxb;  // CTA tasks; x blocks (of kWarps planes) per row
     unsigned ychunk;       // consecutive y rows a CTA sweeps before jumping
+    unsigned plane32;      // plane_bytes (all planes of one sample stay below 4 GiB: 32-bit texel offsets)
+    unsigned magic_full, magic_last;   // ceil(2^16 / steps) for a full / the last z segment: lane / steps without a division
     int warp_smem;         // bytes of shared memory per warp
     int rec_bytes;         // bytes of one voxel record: V x float4 weights, then VP x int offsets
     int off_tile;          // byte offset of the output tile inside a warp's smem
@@ -80,7 +83,7 @@ struct UnprojParams {
 };
 
 struct ViewCell {
-    int off;               // pixel offset of the nw corner inside a padded plane
+    unsigned off;          // byte offset of the nw corner inside a padded plane
     float w00, w01, w10, w11;
 };
 
@@ -158,7 +161,7 @@ __device__ __forceinline__ u64 div_const2(u64 xy, u64 nd /*(-dx,-dy)*/, u64 rd /
 
 // models/aggregation.py:38-51 + ATen grid_sampler unnormalize/compute_interp_params
 __device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1, const float4 &P2,
-                                              float X, float Y, float Z, const UnprojParams &p)
+                                              float X, float Y, float Z, const UnprojParams &p, int lpb)
 {
     // [X Y Z 1] . P rows 0,1 (packed) and row 2: mul, fma, fma, add in k order
     u64 hw = mul2(pk(X, X), pk(P0.x, P1.x));
@@ -195,7 +198,7 @@ __device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1
     const f2 bot = upk(mul2(pk(fr.y, fr.y), ew));                // n*e, n*w
     ViewCell c;
     c.w00 = top.x; c.w01 = top.y; c.w10 = bot.x; c.w11 = bot.y;
-    c.off = (y0 + kBorder) * p.Wp + (x0 + kBorder);
+    c.off = (unsigned)((y0 + kBorder) * p.Wp + (x0 + kBorder)) << lpb;
     if (invalid) {                                   // :62 zero out non-valid points
         c.off = 0;                                   // four border texels: exact +0
         c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
@@ -362,13 +365,19 @@ unproject_kernel(const UnprojParams p)
     // all CTAs work on neighbouring chunks (one sample's maps stay in L2) and a CTA's
     // consecutive tasks share texel rows in L1.
     const unsigned nchunk = (p.ntasks + p.ychunk - 1) / p.ychunk;
-    for (unsigned ck = blockIdx.x; ck < nchunk; ck += gridDim.x)
-    for (unsigned ct = ck * p.ychunk; ct < min(p.ntasks, (ck + 1) * p.ychunk); ++ct) {
-    unsigned t = ct / (unsigned)p.gy;                // task -> (b, z segment, x block, y)
-    const int vy = (int)(ct - t * (unsigned)p.gy);
-    const unsigned xb = t % p.nxb; t /= p.nxb;
-    const int seg = (int)(t % (unsigned)p.nseg);
-    const int b = p.b0 + (int)(t / (unsigned)p.nseg);
+    for (unsigned ck = blockIdx.x; ck < nchunk; ck += gridDim.x) {
+    unsigned ct = ck * p.ychunk;
+    const unsigned ct_end = min(p.ntasks, ct + p.ychunk);
+    // task -> (b, z segment, x block, y): divisions once per chunk, then counted up
+    unsigned t = ct / (unsigned)p.gy;
+    int vy = (int)(ct - t * (unsigned)p.gy);
+    unsigned xb = t % p.nxb; t /= p.nxb;
+    int seg = (int)(t % (unsigned)p.nseg);
+    int b = p.b0 + (int)(t / (unsigned)p.nseg);
+    auto next_task = [&]() {
+        if (++vy == p.gy) { vy = 0; if (++xb == p.nxb) { xb = 0; if (++seg == p.nseg) { seg = 0; ++b; } } }
+    };
+    for (; ct < ct_end; ++ct, next_task()) {
     const int xi = (int)xb * kWarps + warp;
     if (xi >= p.nx) continue;                        // padding of the last x block
     const int vx = p.x_lo + xi;
@@ -399,13 +408,15 @@ unproject_kernel(const UnprojParams p)
             Y = __fadd_rn(rot_row(__ldg(R + 3), __ldg(R + 4), __ldg(R + 5), d0, d1, d2), c1);
             Z = __fadd_rn(rot_row(__ldg(R + 6), __ldg(R + 7), __ldg(R + 8), d0, d1, d2), c2);
         }
-        unsigned char *rec = recs + lane * rec_bytes + (lane / steps) * 16;
+        // lane / steps by multiplication (exact for lane < 32, steps <= 32)
+        const unsigned g_of_lane = ((unsigned)lane * (zn == p.lz ? p.magic_full : p.magic_last)) >> 16;
+        unsigned char *rec = recs + lane * rec_bytes + g_of_lane * 16;
         const float4 *Pb = reinterpret_cast<const float4 *>(p.proj + (size_t)b * p.V * 12);
         auto one_view = [&](int v) {
             const float4 P0 = __ldg(Pb + 3 * v), P1 = __ldg(Pb + 3 * v + 1), P2 = __ldg(Pb + 3 * v + 2);
-            const ViewCell c = make_cell(P0, P1, P2, X, Y, Z, p);
+            const ViewCell c = make_cell(P0, P1, P2, X, Y, Z, p, lpb);
             reinterpret_cast<float4 *>(rec)[v] = make_float4(c.w00, c.w01, c.w10, c.w11);
-            reinterpret_cast<int *>(rec + wbytes)[v] = mine ? c.off : -1;
+            reinterpret_cast<unsigned *>(rec + wbytes)[v] = (v == 0 && !mine) ? kNotMine : c.off;
         };
         if (EXACT) {                                 // independent chains of all views interleave
 #pragma unroll
@@ -424,29 +435,33 @@ unproject_kernel(const UnprojParams p)
 #endif
         constexpr int TV = CACHE ? (VMAX < 4 ? VMAX : 4) : (VMAX < MVHMR_TV ? VMAX : MVHMR_TV);   // views whose texels are in registers at once
         uint4 tex[TV][4];
-        int cur[TV];
+        unsigned cur[TV];
 #pragma unroll
-        for (int v = 0; v < TV; ++v) cur[v] = -2;
+        for (int v = 0; v < TV; ++v) cur[v] = 1u;                  // no texel offset is odd
 
-        // gathers of up to TV views [v0, v0+nv) for the voxel whose record is r; returns false if
-        // the voxel is outside the shard window
-        auto gather = [&](const unsigned char *r, int v0, int nv) -> bool {
-            int off[4];
+        // offsets of views [v0, v0+TV) from the voxel record r
+        auto load_off = [&](const unsigned char *r, int v0, unsigned *off) {
             if (TV == 4) {
-                const int4 o4 = *reinterpret_cast<const int4 *>(r + wbytes + v0 * 4);
+                const uint4 o4 = *reinterpret_cast<const uint4 *>(r + wbytes + v0 * 4);
                 off[0] = o4.x; off[1] = o4.y; off[2] = o4.z; off[3] = o4.w;
             } else {
 #pragma unroll
-                for (int v = 0; v < TV; ++v) off[v] = *reinterpret_cast<const int *>(r + wbytes + (v0 + v) * 4);
+                for (int v = 0; v < TV; ++v) off[v] = *reinterpret_cast<const unsigned *>(r + wbytes + (v0 + v) * 4);
             }
+        };
+        // gathers of up to TV views [v0, v0+nv) at the given offsets; returns false if the voxel is
+        // outside the shard window
+        auto gather_off = [&](const unsigned *off, int v0, int nv) -> bool {
+            const bool inwin = off[0] != kNotMine;                 // only view 0 ever carries the flag
 #pragma unroll
             for (int v = 0; v < TV; ++v) {
                 if (EXACT || v < nv) {
-                    const int o = max(off[v], 0);
+                    const unsigned o = (v == 0 && !inwin) ? 0u : off[v];
                     if (!CACHE || o != cur[v]) {
-                        // view plane offset is warp-uniform; only the cell offset is per lane
-                        const char *q0 = lane_base + ((size_t)(v0 + v) * p.plane_bytes + ((size_t)(unsigned)o << lpb));
-                        const char *q1 = q0 + row;
+                        // 32-bit offset inside the sample's planes: view plane (warp-uniform) + cell
+                        const unsigned t = o + (unsigned)(v0 + v) * p.plane32;
+                        const char *q0 = lane_base + t;
+                        const char *q1 = lane_base + (t + row);
                         tex[v][0] = __ldg(reinterpret_cast<const uint4 *>(q0));
                         tex[v][1] = __ldg(reinterpret_cast<const uint4 *>(q0 + px));
                         tex[v][2] = __ldg(reinterpret_cast<const uint4 *>(q1));
@@ -455,22 +470,36 @@ unproject_kernel(const UnprojParams p)
                     }
                 }
             }
-            return off[0] >= 0;
+            return inwin;
+        };
+        auto gather = [&](const unsigned char *r, int v0, int nv) -> bool {
+            unsigned off[4];
+            load_off(r, v0, off);
+            return gather_off(off, v0, nv);
+        };
+        // row zl of the tile, vector position swizzled by z
+        auto emit = [&](int zl, const Fuse2<METHOD, VMAX, EXACT> *fz) {
+#pragma unroll
+            for (int h = 0; h < NP / 2; ++h) {
+                const f2 r0 = fz[2 * h].result(Vf), r1 = fz[2 * h + 1].result(Vf);
+                const int vec = BF16 ? 2 * chunk + h : chunk;
+                tile[zl * nvec + (vec ^ (zl & (nvec - 1)))] = make_float4(r0.x, r0.y, r1.x, r1.y);
+            }
         };
 
         // ---- phase B: each lane group walks its run of consecutive z voxels ----
         const unsigned char *rec = recs + (grp * steps) * rec_bytes + grp * 16;
         int zl = grp * steps;
-        bool store_next = false;
         const bool piped = single && CACHE && VMAX <= 4;   // the cached path software-pipelines its gathers
-        if (piped) store_next = gather(zl < zn ? rec : recs, 0, p.V) && (zl < zn);
-        for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
-            const unsigned char *r = zl < zn ? rec : recs;
-            Fuse2<METHOD, VMAX, EXACT> fz[NP];
-            bool store = store_next;
-            if (piped) {
-                // software pipeline: blend this voxel, issue the next voxel's gathers, then do the
-                // view fusion (exp, sums) while those loads are in flight
+        if (piped) {
+            // software pipeline: blend this voxel, issue the next voxel's gathers, then do the view
+            // fusion (exp, sums) while those loads are in flight.  (Also prefetching the next
+            // voxel's weights and the offsets after that costs registers and was slower.)
+            bool store_next = gather(zl < zn ? rec : recs, 0, p.V) && (zl < zn);
+            for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
+                const unsigned char *r = zl < zn ? rec : recs;
+                Fuse2<METHOD, VMAX, EXACT> fz[NP];
+                const bool store = store_next;
                 u64 s[VMAX][NP];
 #pragma unroll
                 for (int v = 0; v < TV; ++v)
@@ -480,8 +509,13 @@ unproject_kernel(const UnprojParams p)
                 if (st + 1 < steps) store_next = gather(zl + 1 < zn ? rec + rec_bytes : recs, 0, p.V) && (zl + 1 < zn);
 #pragma unroll
                 for (int i = 0; i < NP; ++i) fz[i].absorb(&s[0][i], NP, p.V, true);
-            } else {
-                store = zl < zn;
+                if (store) emit(zl, fz);
+            }
+        } else {
+            for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
+                const unsigned char *r = zl < zn ? rec : recs;
+                Fuse2<METHOD, VMAX, EXACT> fz[NP];
+                bool store = zl < zn;
                 for (int vb = 0; vb < p.V; vb += VMAX) {
                     const int nv = EXACT ? VMAX : min(VMAX, p.V - vb);
                     u64 s[VMAX][NP];
@@ -501,14 +535,7 @@ unproject_kernel(const UnprojParams p)
 #pragma unroll
                     for (int i = 0; i < NP; ++i) fz[i].absorb(&s[0][i], NP, nv, vb == 0);
                 }
-            }
-            if (store) {                                     // row zl of the tile, vector position swizzled by z
-#pragma unroll
-                for (int h = 0; h < NP / 2; ++h) {
-                    const f2 r0 = fz[2 * h].result(Vf), r1 = fz[2 * h + 1].result(Vf);
-                    const int vec = BF16 ? 2 * chunk + h : chunk;
-                    tile[zl * nvec + (vec ^ (zl & (nvec - 1)))] = make_float4(r0.x, r0.y, r1.x, r1.y);
-                }
+                if (store) emit(zl, fz);
             }
         }
         __syncwarp();
@@ -539,7 +566,8 @@ unproject_kernel(const UnprojParams p)
         __syncwarp();
     }
     }   // task body
-    }   // persistent task loop
+    }   // tasks of one chunk
+    }   // persistent chunk loop
 }
 
 // NCHW -> pixel-major padded planes.  One CTA per padded row: channel planes are
@@ -799,12 +827,23 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     p.nchunks = nchunks;
     p.lpb = ilog2_exact(nchunks) + 4;
     p.plane_bytes = ((long long)(H + 2 * kBorder) * p.Wp) << p.lpb;
+    if ((long long)V * p.plane_bytes + ((long long)(p.Wp + 1) << p.lpb) + 16LL * nchunks >= (1LL << 32))
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: the padded feature maps of one sample must stay below 4 GiB");
+    p.plane32 = (unsigned)p.plane_bytes;
     p.V = V; p.VP = VP; p.C = C; p.W = W; p.H = H; p.b0 = b0; p.nb = b1 - b0;
     p.gx = gx; p.gy = gy; p.gz = gz;
     const long long yz = (long long)gy * gz;
     p.x_lo = (int)(n0 / yz);
     p.nx = (int)((n1 - 1) / yz) - p.x_lo + 1;
     p.lz = lz; p.nseg = (gz + lz - 1) / lz;
+    {
+        const int ngroups = 32 / nch_pass;
+        const int steps_full = (lz + ngroups - 1) / ngroups;
+        const int zlast = gz - (p.nseg - 1) * lz;
+        const int steps_last = (zlast + ngroups - 1) / ngroups;
+        p.magic_full = (65536u + steps_full - 1) / steps_full;
+        p.magic_last = (65536u + steps_last - 1) / steps_last;
+    }
     p.warp_smem = warp_smem; p.rec_bytes = rec_bytes; p.off_tile = off_tile;
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
