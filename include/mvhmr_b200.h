@@ -57,6 +57,13 @@ extern "C" {
 #define MVHMR_LAYOUT_NCHW 0   /* (B,V,C,H,W) as the reference passes them      */
 #define MVHMR_LAYOUT_PACKED 1 /* already in the library's gather layout, i.e.  */
                               /* the output of mvhmr_pack_features             */
+#define MVHMR_LAYOUT_NHWC 2   /* (B,V,H,W,C) channels-last, gathered in place  */
+                              /* (no pack pass, no workspace): what a cuDNN    */
+                              /* 1x1 conv emits for a channels_last tensor.    */
+                              /* Needs C*elemsize = 16*2^k bytes, H,W >= 2,    */
+                              /* 16-byte alignment; texels must be finite (a   */
+                              /* corner outside the map is realised as         */
+                              /* weight*0 times a real texel).                 */
 
 int mvhmr_abi_version(void);
 

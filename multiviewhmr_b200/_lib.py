@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("MVHMR_LIB") or os.path.join(_HERE, "lib", "libmvhmr_b
 OK, ERR_INVALID_ARGUMENT, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3
 SUM, MEAN, MAX, SOFTMAX = 0, 1, 2, 3
 F32, BF16 = 0, 1
-LAYOUT_NCHW, LAYOUT_PACKED = 0, 1
+LAYOUT_NCHW, LAYOUT_PACKED, LAYOUT_NHWC = 0, 1, 2
 METHODS = {"sum": SUM, "mean": MEAN, "max": MAX, "softmax": SOFTMAX}
 
 _vp, _i, _ll, _sz, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_uint

@@ -37,6 +37,16 @@ def _feat_dtype(features):
     raise TypeError("multiviewhmr_b200: feature maps must be float32 or bfloat16, got %s" % features.dtype)
 
 
+def _is_channels_last(features):
+    """True if the (B,V,C,H,W) tensor is physically (B,V,H,W,C) and its pixels can be
+    gathered in place (`MVHMR_LAYOUT_NHWC` in include/mvhmr_b200.h)."""
+    B, V, C, H, W = features.shape
+    pixel = C * features.element_size()
+    if pixel < 16 or pixel & (pixel - 1) or H < 2 or W < 2 or features.data_ptr() % 16:
+        return False
+    return tuple(features.stride()) == (V * H * W * C, H * W * C, 1, W * C, C)
+
+
 def pack_features(features):
     """(B,V,C,H,W) -> the library's gather layout (opaque uint8 tensor).
     Lets a caller that reuses one set of feature maps for several grids pay the
@@ -103,7 +113,11 @@ def _launch_unprojection(features, proj_matricies, shape, aggregation_method, wi
         raise ValueError("out must be a contiguous float32 (B,C,Gx,Gy,Gz) tensor on %s" % dev)
     b0, b1, n0, n1 = (0, B, 0, N) if window is None else (int(v) for v in window)
     with torch.cuda.device(dev):
-        if packed is None:
+        if packed is None and _is_channels_last(features):
+            # (B,V,C,H,W) view of channels-last maps (what a channels_last 1x1 conv emits):
+            # gathered in place, no layout pass
+            feats, layout, ws_bytes, ws_ptr = features.detach(), _lib.LAYOUT_NHWC, 0, None
+        elif packed is None:
             feats = features.detach().contiguous()
             layout = _lib.LAYOUT_NCHW
             ws_bytes = L.mvhmr_unproject_workspace_bytes(dt, layout, B, V, C, H, W)
@@ -283,6 +297,8 @@ class VolumeGenerator(nn.Module):
         self.kind = kind
         self.dataset = dataset
         self.fuse_grid = True       # not a reference attribute: build the cuboid grid inside the fused kernel
+        self.channels_last = True   # not a reference attribute: the 1x1 squeeze emits (B,V,H,W,C) maps that the
+                                    # fused kernel gathers in place (no pack pass); inference only
         self.to(device)
 
     def _projections(self, batch, images_shape, features_shape, n_views, batch_size):
@@ -296,6 +312,26 @@ class VolumeGenerator(nn.Module):
                 cam.update_after_resize(images_shape, features_shape)
                 P[b, v] = cam.projection
         return P
+
+    def _squeeze_channels(self, features, batch_size, n_views):
+        """`:189-191` the 1x1 conv over all views.  Without autograd the same contraction runs as one
+        batched GEMM whose output is pixel-major, (B,V,H,W,C) — the layout the fused kernel gathers
+        in place (`MVHMR_LAYOUT_NHWC`), so neither a transposition nor the pack pass is paid."""
+        conv = self.process_feature[0]
+        Cin, H, W = features.shape[-3:]
+        Cout = conv.out_channels
+        pixel = Cout * features.element_size()
+        needs_grad = torch.is_grad_enabled() and (features.requires_grad or conv.weight.requires_grad)
+        if (self.channels_last and not needs_grad and conv.bias is not None and features.dtype == conv.weight.dtype
+                and pixel >= 16 and pixel & (pixel - 1) == 0 and H >= 2 and W >= 2):
+            BV = batch_size * n_views
+            x = features.reshape(BV, Cin, H * W).transpose(1, 2)                    # (BV, HW, Cin), a view
+            wt = conv.weight.detach().view(Cout, Cin).t().unsqueeze(0).expand(BV, Cin, Cout)
+            y = torch.baddbmm(conv.bias.detach().view(1, 1, Cout), x, wt)           # (BV, HW, Cout) contiguous
+            return y.view(batch_size, n_views, H, W, Cout).permute(0, 1, 4, 2, 3)
+        features = features.view(-1, *features.shape[2:])
+        features = self.process_feature(features)
+        return features.view(batch_size, n_views, *features.shape[1:])
 
     def forward(self, features, proj_matricies, batch, use_gt=True):
         device = features.device
@@ -323,9 +359,7 @@ class VolumeGenerator(nn.Module):
                     proj_org[b], images_center).numpy()
             else:
                 centers[b] = np.asarray(batch['keypoints_3d'][b])[6, :3]          # `:180-181`
-        features = features.view(-1, *features.shape[2:])
-        features = self.process_feature(features)
-        features = features.view(batch_size, n_views, *features.shape[1:])
+        features = self._squeeze_channels(features, batch_size, n_views)
 
         if self.fuse_grid:      # coordinates generated inside the kernel, bit-identical to the two-step path
             return unprojection_grid(features, proj, centers, rots, self.volume_size, self.cuboid_side,

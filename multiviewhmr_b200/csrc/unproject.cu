@@ -66,6 +66,7 @@ struct UnprojParams {
     long long plane_bytes; // Hp * Wp * pixel bytes
     int V, VP, C, W, H, Wp;
     int lpb;               // log2(pixel bytes)
+    int border;            // zero texels around the map: kBorder (packed layout) or 0 (caller's channels-last maps)
     int nchunks;           // 16-byte vectors per pixel (power of two)
     int b0, nb;
     int gx, gy, gz;
@@ -198,7 +199,36 @@ __device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1
     const f2 bot = upk(mul2(pk(fr.y, fr.y), ew));                // n*e, n*w
     ViewCell c;
     c.w00 = top.x; c.w01 = top.y; c.w10 = bot.x; c.w11 = bot.y;
-    c.off = (unsigned)((y0 + kBorder) * p.Wp + (x0 + kBorder)) << lpb;
+    if (p.border == 0) {
+        // Channels-last maps without a zero border.  A corner outside the map contributes
+        // 0 * weight in the reference; here the cell is moved inside the map, the weights of
+        // the corners that are really there move with their texels and every other slot gets
+        // weight * 0 (keeps NaN / inf weights poisonous, and the order of the non-zero
+        // terms of the blend is unchanged).  Needs W, H >= 2.
+        if (x0 < 0 || x0 > p.W - 2) {
+            const bool l_in = (x0 == p.W - 1), r_in = (x0 == -1);   // which real column survives
+            const float a0 = c.w00, a1 = c.w10;                     // weights of column x0
+            c.w00 = r_in ? c.w01 : __fmul_rn(c.w01, 0.0f);
+            c.w10 = r_in ? c.w11 : __fmul_rn(c.w11, 0.0f);
+            c.w01 = l_in ? a0 : __fmul_rn(a0, 0.0f);
+            c.w11 = l_in ? a1 : __fmul_rn(a1, 0.0f);
+            if (l_in) { c.w00 = __fmul_rn(c.w00, 0.0f); c.w10 = __fmul_rn(c.w10, 0.0f); }
+            if (r_in) { c.w01 = __fmul_rn(c.w01, 0.0f); c.w11 = __fmul_rn(c.w11, 0.0f); }
+            x0 = min(max(x0, 0), p.W - 2);
+        }
+        if (y0 < 0 || y0 > p.H - 2) {
+            const bool t_in = (y0 == p.H - 1), b_in = (y0 == -1);   // which real row survives
+            const float a0 = c.w00, a1 = c.w01;                     // weights of row y0
+            c.w00 = b_in ? c.w10 : __fmul_rn(c.w10, 0.0f);
+            c.w01 = b_in ? c.w11 : __fmul_rn(c.w11, 0.0f);
+            c.w10 = t_in ? a0 : __fmul_rn(a0, 0.0f);
+            c.w11 = t_in ? a1 : __fmul_rn(a1, 0.0f);
+            if (t_in) { c.w00 = __fmul_rn(c.w00, 0.0f); c.w01 = __fmul_rn(c.w01, 0.0f); }
+            if (b_in) { c.w10 = __fmul_rn(c.w10, 0.0f); c.w11 = __fmul_rn(c.w11, 0.0f); }
+            y0 = min(max(y0, 0), p.H - 2);
+        }
+    }
+    c.off = (unsigned)((y0 + p.border) * p.Wp + (x0 + p.border)) << lpb;
     if (invalid) {                                   // :62 zero out non-valid points
         c.off = 0;                                   // four border texels: exact +0
         c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
@@ -704,7 +734,7 @@ extern "C" size_t mvhmr_packed_bytes(int feat_dtype, int BV, int C, int H, int W
 
 extern "C" size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, int V, int C, int H, int W)
 {
-    if (feat_layout == MVHMR_LAYOUT_PACKED) return 0;
+    if (feat_layout == MVHMR_LAYOUT_PACKED || feat_layout == MVHMR_LAYOUT_NHWC) return 0;
     if (B < 0 || V < 0) return 0;
     return mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);
 }
@@ -743,7 +773,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "Unknown aggregation_method: %d", method);
     if (feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: unknown feat_dtype %d", feat_dtype);
-    if (feat_layout != MVHMR_LAYOUT_NCHW && feat_layout != MVHMR_LAYOUT_PACKED)
+    if (feat_layout != MVHMR_LAYOUT_NCHW && feat_layout != MVHMR_LAYOUT_PACKED && feat_layout != MVHMR_LAYOUT_NHWC)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: unknown feat_layout %d", feat_layout);
     if (B < 0 || V < 1 || C < 1 || H < 1 || W < 1 || gx < 1 || gy < 1 || gz < 1)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: bad shape B=%d V=%d C=%d H=%d W=%d G=(%d,%d,%d)",
@@ -810,7 +840,15 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         if (rc != MVHMR_OK) return rc;
         packed = (const char *)ws;
     } else {
-        if ((uintptr_t)feats & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: packed features must be 16-byte aligned");
+        if ((uintptr_t)feats & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: packed / channels-last features must be 16-byte aligned");
+        if (feat_layout == MVHMR_LAYOUT_NHWC) {
+            // the caller's (B,V,H,W,C) maps are gathered in place: a pixel must be a power-of-two
+            // number of 16-byte vectors and the cell logic needs two texels per axis
+            if (C != nchunks * (bf ? 8 : 4))
+                return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: channels-last input needs C = %d * 2^k, got C=%d (use the NCHW layout)", bf ? 8 : 4, C);
+            if (H < 2 || W < 2)
+                return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: channels-last input needs H, W >= 2 (use the NCHW layout)");
+        }
         packed = (const char *)feats;
     }
 
@@ -823,10 +861,11 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         p.gstep[k] = grid_desc ? grid_desc->step[k] : 0.0f;
     }
     p.n0 = n0; p.n1 = n1; p.n_origin = n_origin; p.n_extent = n_extent;
-    p.Wp = W + 2 * kBorder;
+    p.border = (feat_layout == MVHMR_LAYOUT_NHWC) ? 0 : kBorder;
+    p.Wp = W + 2 * p.border;
     p.nchunks = nchunks;
     p.lpb = ilog2_exact(nchunks) + 4;
-    p.plane_bytes = ((long long)(H + 2 * kBorder) * p.Wp) << p.lpb;
+    p.plane_bytes = ((long long)(H + 2 * p.border) * p.Wp) << p.lpb;
     if ((long long)V * p.plane_bytes + ((long long)(p.Wp + 1) << p.lpb) + 16LL * nchunks >= (1LL << 32))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: the padded feature maps of one sample must stay below 4 GiB");
     p.plane32 = (unsigned)p.plane_bytes;

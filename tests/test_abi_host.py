@@ -64,6 +64,14 @@ def test_argument_validation_needs_no_gpu(built_lib):
     rc = L.mvhmr_unproject_aggregate(*args, _lib.SUM, 0, 1, 0, 32 ** 3, 0, 32 ** 3, 65,
                                      one, 1 << 30, None)
     assert rc == _lib.ERR_INVALID_ARGUMENT and b"tile_hint" in L.mvhmr_last_error()
+    # channels-last input: gathered in place, so the pixel must be 16 * 2^k bytes and the map >= 2x2
+    assert L.mvhmr_unproject_workspace_bytes(_lib.F32, _lib.LAYOUT_NHWC, 8, 4, 32, 96, 96) == 0
+    nhwc = [one, _lib.F32, _lib.LAYOUT_NHWC, one, one, one, 1, 4, 17, 64, 64, 32, 32, 32]
+    rc = L.mvhmr_unproject_aggregate(*nhwc, _lib.SUM, 0, 1, 0, 32 ** 3, 0, 32 ** 3, 0, None, 0, None)
+    assert rc == _lib.ERR_INVALID_ARGUMENT and b"channels-last" in L.mvhmr_last_error()
+    nhwc[8:11] = [32, 1, 64]
+    rc = L.mvhmr_unproject_aggregate(*nhwc, _lib.SUM, 0, 1, 0, 32 ** 3, 0, 32 ** 3, 0, None, 0, None)
+    assert rc == _lib.ERR_INVALID_ARGUMENT and b"H, W >= 2" in L.mvhmr_last_error()
     assert L.mvhmr_soft_argmax3d(one, one, one, 1, 1, 64, None, 0, None) == _lib.ERR_WORKSPACE
     assert L.mvhmr_build_coord_volumes(one, one, one, None, None, 1, 4, 4, 4, None) == _lib.ERR_INVALID_ARGUMENT
     # empty problems succeed without touching the device

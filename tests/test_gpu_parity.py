@@ -54,6 +54,48 @@ def test_golden_vectors(golden, case, method):
         assert rel_l2(got.cpu().numpy(), z["out_" + method]) < 1e-2
 
 
+def channels_last(f):
+    """Same (B,V,C,H,W) values, physically (B,V,H,W,C): what a channels_last 1x1 conv emits."""
+    return f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+
+
+@pytest.mark.parametrize("method", METHODS)
+def test_channels_last_maps_are_gathered_in_place(golden, method):
+    """MVHMR_LAYOUT_NHWC: no pack pass, no zero border — corners outside the map
+    are realised by moving the cell inside and zeroing weights.  Must equal the NCHW path bit
+    for bit, including cells that straddle or leave the map (unproj_edge)."""
+    z = golden("unproj_edge")
+    f, P, cv = cuda(z["features"], z["proj"], z["coord_volumes"])
+    B, V, C, H, W = f.shape
+    Cp = 4
+    while Cp < C:
+        Cp *= 2
+    fpad = torch.zeros(B, V, Cp, H, W, device=DEV)
+    fpad[:, :, :C] = f
+    fcl = channels_last(fpad)
+    assert agg._is_channels_last(fcl) and not agg._is_channels_last(fpad)
+    got = agg.unprojection(fcl, P, cv, method)
+    assert torch.equal(got, agg.unprojection(fpad, P, cv, method))
+    if "out_" + method in z.files:
+        check_volume(got[:, :C], z["out_" + method], method)
+    # bf16 storage and the fused-grid entry point go through the same cell logic
+    w = syn.CONFIGS["cfg1"]
+    f1, P1, cv1, c1 = syn.make_inputs(w, theta=0.4)
+    P1 = P1.clone()
+    P1[:, :, :2] *= 1.7                                    # pixel coordinates x1.7: many voxels leave the maps
+    f1, P1, cv1 = cuda(f1, P1, cv1)
+    for ft in (f1, f1.bfloat16()):
+        fcl = channels_last(ft)
+        assert agg._is_channels_last(fcl)
+        assert torch.equal(agg.unprojection(fcl, P1, cv1, method), agg.unprojection(ft, P1, cv1, method))
+    # tiny maps: every cell touches an edge
+    g = torch.Generator().manual_seed(5)
+    ft = torch.randn(2, 3, 8, 2, 3, generator=g).to(DEV)
+    Pt = syn.make_projections(2, 3, 2, 3).to(DEV)
+    cvt = cv1[:1, ::4, ::4, ::4].expand(2, -1, -1, -1, -1).contiguous()
+    assert torch.equal(agg.unprojection(channels_last(ft), Pt, cvt, method), agg.unprojection(ft, Pt, cvt, method))
+
+
 @pytest.mark.parametrize("method", METHODS)
 def test_cfg1_against_oracle_and_golden_slice(golden, method):
     w = syn.CONFIGS["cfg1"]
@@ -251,6 +293,17 @@ def test_volume_generator_module(golden, case):
     with torch.no_grad():
         vol_fused = vg(*cuda(z["features"], z["proj_in"]), batch)
     assert torch.equal(vol_fused, vol)
+    # the squeeze normally runs as a batched GEMM that emits channels-last maps (gathered in place);
+    # the cuDNN conv + pack route must agree to fp32 rounding of the 1x1 contraction
+    assert seen["feats"].shape == z["used_features"].shape
+    channels = seen["feats"].shape[2] * 4
+    assert agg._is_channels_last(seen["feats"]) == (channels >= 16 and channels & (channels - 1) == 0)
+    vg.channels_last = False
+    np.random.seed(int(z["np_seed"]))
+    with torch.no_grad():
+        vol_conv = vg(*cuda(z["features"], z["proj_in"]), batch)
+    assert rel_l2(vol_conv.cpu().numpy(), z["volumes"]) < SPEC_TOL_FP32
+    assert rel_l2(vol_conv.cpu().numpy(), vol.cpu().numpy()) < SPEC_TOL_FP32
 
 
 def test_geometry_kernels_are_bit_exact(golden):
