@@ -149,6 +149,46 @@ def test_ragged_shapes(B, V, C, H, W, G, method):
     check_volume(got, oracle.unprojection(f, P, cv, method), method)
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzzed_shapes_layouts_and_windows(seed):
+    """Seeded random problems (non-cubic grids, odd channel counts, behind-camera views, far-away
+    voxels, bf16 storage, channels-last maps, shard windows) against the C restatement."""
+    rng = np.random.RandomState(1000 + seed)
+    B, V = int(rng.randint(1, 4)), int(rng.choice([1, 2, 3, 4, 5, 8, 11]))
+    C = int(rng.choice([1, 3, 4, 8, 17, 32, 40]))
+    H, W = int(rng.randint(2, 40)), int(rng.randint(2, 40))
+    G = tuple(int(x) for x in rng.randint(1, 37, size=3))
+    method = METHODS[seed % 4]
+    bf16 = bool(rng.randint(2))
+    g = torch.Generator().manual_seed(seed)
+    f = torch.randn(B, V, C, H, W, generator=g)
+    if bf16:
+        f = f.bfloat16().float()
+    P = syn.make_projections(B, V, H, W, behind_views=(0,) if rng.randint(2) else ())
+    cv = (torch.rand(B, *G, 3, generator=g) - 0.5) * float(rng.choice([800.0, 2600.0, 9000.0]))
+    ref = oracle.unprojection(f, P, cv, method)
+    fd, Pd, cvd = cuda(f, P, cv)
+    if bf16:
+        fd = fd.bfloat16()
+    check_volume(agg.unprojection(fd, Pd, cvd, method), ref, method)
+    pixel = C * fd.element_size()
+    if pixel >= 16 and pixel & (pixel - 1) == 0:                     # eligible for the in-place layout
+        fcl = channels_last(fd)
+        assert agg._is_channels_last(fcl)
+        check_volume(agg.unprojection(fcl, Pd, cvd, method), ref, method)
+    # a random shard window into a NaN-poisoned buffer: inside == reference, outside untouched
+    N = G[0] * G[1] * G[2]
+    b0 = int(rng.randint(0, B)); b1 = int(rng.randint(b0 + 1, B + 1))
+    n0 = int(rng.randint(0, N)); n1 = int(rng.randint(n0 + 1, N + 1))
+    out = torch.full((B, C) + G, float("nan"), device=DEV)
+    agg.unprojection(fd, Pd, cvd, method, window=(b0, b1, n0, n1), out=out)
+    got = out.cpu().numpy().reshape(B, C, N)
+    check_volume(got[b0:b1, :, n0:n1], ref.reshape(B, C, N)[b0:b1, :, n0:n1], method)
+    mask = np.ones((B, 1, N), bool)
+    mask[b0:b1, :, n0:n1] = False
+    assert np.isnan(got[np.broadcast_to(mask, got.shape)]).all()
+
+
 @pytest.mark.parametrize("lz", ["1", "5", "8", "24", "32"])
 def test_z_segment_length_does_not_change_results(monkeypatch, lz):
     w = syn.Workload("t", B=2, V=4, C=8, H=32, W=32, G=24)
