@@ -172,6 +172,16 @@ int mvhmr_unproject_aggregate_backward(const float *grad_out, const void *feats,
                                        const float *proj, const float *coord, float *grad_feats,
                                        int B, int V, int C, int H, int W, long long N, int method, void *stream);
 
+/* The same gradient, fast path: the forward's lane-group mapping, scatter with
+ * red.global.add.v4.f32 into pixel-major planes inside the workspace, then one
+ * un-pack pass.  grad_feats is OVERWRITTEN (no zeroing by the caller).  ws of
+ * mvhmr_unproject_backward_workspace_bytes(...) bytes, 16-byte aligned. */
+size_t mvhmr_unproject_backward_workspace_bytes(int feat_dtype, int B, int V, int C, int H, int W, int method);
+int mvhmr_unproject_aggregate_backward_ws(const float *grad_out, const void *feats, int feat_dtype,
+                                          const float *proj, const float *coord, float *grad_feats,
+                                          int B, int V, int C, int H, int W, long long N, int method,
+                                          void *ws, size_t ws_bytes, void *stream);
+
 /* Self-test: runs the kernel's two exact-division shortcuts (division by a launch
  * constant via reciprocal + FMA correction; shared-reciprocal division) for ALL
  * 2^32 numerators against div.rn.f32 with divisor d and ADDS the number of

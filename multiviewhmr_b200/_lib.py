@@ -35,6 +35,8 @@ SIGNATURES = {
     "mvhmr_unproject_aggregate_grid": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                             _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
     "mvhmr_unproject_aggregate_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp]),
+    "mvhmr_unproject_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "mvhmr_unproject_aggregate_backward_ws": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp, _sz, _vp]),
     "mvhmr_selftest_division": (_i, [ctypes.c_float, _vp, _vp]),
     "mvhmr_soft_argmax3d_num_slices": (_i, [_ll]),
     "mvhmr_soft_argmax3d_workspace_bytes": (_sz, [_i, _i, _ll]),

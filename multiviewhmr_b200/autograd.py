@@ -24,20 +24,39 @@ class _Unprojection(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         features, proj_matricies, coord_volumes = ctx.saved_tensors
-        from .aggregation import _feat_dtype
-        dev = features.device
-        B, V, C, H, W = features.shape
-        N = coord_volumes.shape[1] * coord_volumes.shape[2] * coord_volumes.shape[3]
-        g = grad_out.detach().float().contiguous()
-        feats = features.detach().contiguous()
-        proj = proj_matricies.detach().float().contiguous()
-        coord = coord_volumes.detach().float().contiguous()
-        gf = torch.zeros((B, V, C, H, W), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(_lib.load().mvhmr_unproject_aggregate_backward(
-                _lib.ptr(g), _lib.ptr(feats), _feat_dtype(features), _lib.ptr(proj), _lib.ptr(coord), _lib.ptr(gf),
-                B, V, C, H, W, N, _lib.METHODS[ctx.method], _lib.stream_ptr(dev)))
+        g, feats, proj, coord = grad_out, features, proj_matricies, coord_volumes
+        gf = unprojection_backward(g, feats, proj, coord, ctx.method)
         return gf.to(features.dtype), None, None, None
+
+
+def unprojection_backward(grad_out, features, proj_matricies, coord_volumes, aggregation_method, simple=False):
+    """Gradient of `unprojection` w.r.t. `features`: (B,C,...) fp32 x (B,V,C,H,W) -> (B,V,C,H,W) fp32.
+    `simple=True` runs the first, thread-per-voxel kernel (kept as an independent implementation
+    for the tests; V <= 64)."""
+    from .aggregation import _feat_dtype
+    dev = _lib.require_cuda(grad_out, features, proj_matricies, coord_volumes)
+    B, V, C, H, W = features.shape
+    N = coord_volumes.numel() // (3 * B) if B else 0
+    L = _lib.load()
+    dt, m = _feat_dtype(features), _lib.METHODS[aggregation_method]
+    g = grad_out.detach().float().contiguous()
+    feats = features.detach().contiguous()
+    proj = proj_matricies.detach().float().contiguous()
+    coord = coord_volumes.detach().float().contiguous()
+    with torch.cuda.device(dev):
+        if simple:
+            gf = torch.zeros((B, V, C, H, W), dtype=torch.float32, device=dev)
+            _lib.check(L.mvhmr_unproject_aggregate_backward(
+                _lib.ptr(g), _lib.ptr(feats), dt, _lib.ptr(proj), _lib.ptr(coord), _lib.ptr(gf),
+                B, V, C, H, W, N, m, _lib.stream_ptr(dev)))
+            return gf
+        gf = torch.empty((B, V, C, H, W), dtype=torch.float32, device=dev)
+        ws_bytes = L.mvhmr_unproject_backward_workspace_bytes(dt, B, V, C, H, W, m)
+        ws = torch.empty(max(ws_bytes, 16), dtype=torch.uint8, device=dev)
+        _lib.check(L.mvhmr_unproject_aggregate_backward_ws(
+            _lib.ptr(g), _lib.ptr(feats), dt, _lib.ptr(proj), _lib.ptr(coord), _lib.ptr(gf),
+            B, V, C, H, W, N, m, _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+    return gf
 
 
 def unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method):

@@ -29,10 +29,10 @@
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include "mvhmr_common.cuh"
+#include "unproject_device.cuh"
 
 namespace mvhmr {
 
-constexpr int kBorder = 2;
 #ifndef MVHMR_WARPS
 #define MVHMR_WARPS 16
 #endif
@@ -48,246 +48,6 @@ constexpr int kBorder = 2;
 constexpr int kWarps = MVHMR_WARPS;       // warps per CTA: consecutive x planes share their texel footprint in L1
 constexpr unsigned kNotMine = 0xffffffffu;   // view-0 offset of a voxel outside the shard window (real offsets are multiples of 16)
 constexpr int kLzMax = 32;                // voxels of one warp task (z segment): one per lane in phase A
-constexpr int kYRows = 1;                 // consecutive y rows walked by one CTA
-constexpr int kVecPass = 32;              // 16-byte channel vectors handled per pass (at most one per lane)
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kMagic = 12582912.0f;     // 1.5 * 2^23: a float add rounds to integer
-
-struct UnprojParams {
-    const char *packed;    // (B*V, Hp, Wp, CP) pixel-major planes
-    const float *proj;     // (B, V, 3, 4)
-    const float *coord;    // (B, n_extent, 3): voxels [n_origin, n_origin + n_extent); NULL = generate
-    const float *centers;  // (B, 3)   } only when coord == NULL: the grid of
-    const float *rot;      // (B, 3, 3) } models/aggregation.py:135-187 is built in registers
-    float gpos[3], gstep[3];
-    float *out;            // (B, C, n_extent)
-    long long n0, n1;      // voxels computed by this launch
-    long long n_origin, n_extent;
-    long long plane_bytes; // Hp * Wp * pixel bytes
-    int V, VP, C, W, H, Wp;
-    int lpb;               // log2(pixel bytes)
-    int border;            // zero texels around the map: kBorder (packed layout) or 0 (caller's channels-last maps)
-    int nchunks;           // 16-byte vectors per pixel (power of two)
-    int b0, nb;
-    int gx, gy, gz;
-    int x_lo, nx;          // x planes touched by [n0,n1)
-    int lz, nseg;          // z segment length (<= kLzMax) and segments per z row
-    unsigned ntasks, nxb;  // CTA tasks; x blocks (of kWarps planes) per row
-    unsigned ychunk;       // consecutive y rows a CTA sweeps before jumping
-    unsigned plane32;      // plane_bytes (all planes of one sample stay below 4 GiB: 32-bit texel offsets)
-    unsigned magic_full, magic_last;   // ceil(2^16 / steps) for a full / the last z segment: lane / steps without a division
-    int warp_smem;         // bytes of shared memory per warp
-    int rec_bytes;         // bytes of one voxel record: V x float4 weights, then VP x int offsets
-    int off_tile;          // byte offset of the output tile inside a warp's smem
-    float Hf, Wf, sx, sy;  // (float)H, (float)W, (W-1)/2, (H-1)/2
-    float rH, rW;          // RN(1/H), RN(1/W)
-};
-
-struct ViewCell {
-    unsigned off;          // byte offset of the nw corner inside a padded plane
-    float w00, w01, w10, w11;
-};
-
-// ---- packed f32x2 helpers (FFMA2 / FMUL2 / FADD2 on sm_100a) ---------------
-typedef unsigned long long u64;
-struct f2 { float x, y; };
-__device__ __forceinline__ u64 pk(float a, float b)
-{
-    u64 r;
-    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
-    return r;
-}
-__device__ __forceinline__ f2 upk(u64 v)
-{
-    f2 r;
-    asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c)
-{
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
-__device__ __forceinline__ u64 mul2(u64 a, u64 b)
-{
-    u64 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-__device__ __forceinline__ u64 add2(u64 a, u64 b)
-{
-    u64 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-    return d;
-}
-// The x and y pipelines of the projection are identical chains of IEEE operations, so they
-// run as one packed f32x2 stream (each half is a correctly rounded fp32 op; results are
-// bit-identical to the scalar sequence).
-
-// (a.x/b, a.y/b) correctly rounded.  Same instruction sequence as the div.rn.f32 fast path
-// (MUFU.RCP, one Newton step, quotient, exact remainder, correction); operands outside the
-// safe exponent range (including exact zeros) take the library division.
-__device__ __forceinline__ u64 div2_rn(u64 a, float b)
-{
-    const f2 av = upk(a);
-    const float lo = fminf(fminf(fabsf(av.x), fabsf(av.y)), fabsf(b));
-    const float hi = fmaxf(fmaxf(fabsf(av.x), fabsf(av.y)), fabsf(b));
-    if (lo > 1e-30f && hi < 1e30f) {
-        float r;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
-        const float e = __fmaf_rn(-b, r, 1.0f);
-        r = __fmaf_rn(r, e, r);
-        const u64 rr = pk(r, r), nb = pk(-b, -b);
-        const u64 t = mul2(a, rr);
-        const u64 m = fma2(nb, t, a);
-        return fma2(rr, m, t);
-    }
-    return pk(__fdiv_rn(av.x, b), __fdiv_rn(av.y, b));
-}
-
-// (x/dx, y/dy) for launch constants with rd = RN(1/d): q = x*rd, r = x - d*q (exact),
-// q' = q + r*rd is the correctly rounded quotient (Markstein) for operands in the safe
-// range; checked exhaustively for the usual map sizes in the tests.
-__device__ __forceinline__ u64 div_const2(u64 xy, u64 nd /*(-dx,-dy)*/, u64 rd /*(1/dx,1/dy)*/, float dx, float dy)
-{
-    const f2 v = upk(xy);
-    const float lo = fminf(fabsf(v.x), fabsf(v.y)), hi = fmaxf(fabsf(v.x), fabsf(v.y));
-    if (lo > 1e-30f && hi < 1e30f) {
-        const u64 q = mul2(xy, rd);
-        return fma2(fma2(nd, q, xy), rd, q);
-    }
-    return pk(__fdiv_rn(v.x, dx), __fdiv_rn(v.y, dy));
-}
-
-// models/aggregation.py:38-51 + ATen grid_sampler unnormalize/compute_interp_params
-__device__ __forceinline__ ViewCell make_cell(const float4 &P0, const float4 &P1, const float4 &P2,
-                                              float X, float Y, float Z, const UnprojParams &p, int lpb)
-{
-    // [X Y Z 1] . P rows 0,1 (packed) and row 2: mul, fma, fma, add in k order
-    u64 hw = mul2(pk(X, X), pk(P0.x, P1.x));
-    hw = fma2(pk(Y, Y), pk(P0.y, P1.y), hw);
-    hw = fma2(pk(Z, Z), pk(P0.z, P1.z), hw);
-    hw = add2(hw, pk(P0.w, P1.w));
-    const float ww = proj_row(X, Y, Z, P2.x, P2.y, P2.z, P2.w);
-    const bool invalid = ww <= 0.0f;                 // :42 depth must be > 0
-    const float wd = (ww == 0.0f) ? 1.0f : ww;       // :44 not to divide by zero
-    const u64 xy = div2_rn(hw, wd);
-    // :49-50  2*(x/feature_shape[0] - 0.5): x by H, y by W (reference behaviour)
-    const u64 q = div_const2(xy, pk(-p.Hf, -p.Wf), pk(p.rH, p.rW), p.Hf, p.Wf);
-    const u64 g = mul2(pk(2.0f, 2.0f), add2(q, pk(-0.5f, -0.5f)));
-    // align_corners=True: (g + 1) * ((size - 1) / 2)
-    const f2 i = upk(mul2(add2(g, pk(1.0f, 1.0f)), pk(p.sx, p.sy)));
-    // Cell index from the position clamped into the zero border (NaN -> border).
-    // Inside the map clamped == unclamped, so floor and weights are the
-    // reference's; outside, every corner is a zero texel and only finiteness of
-    // the weights matters (0 * NaN = NaN, as in the reference).
-    const float ixc = fminf(fmaxf(i.x, -2.0f), p.Wf), iyc = fminf(fmaxf(i.y, -2.0f), p.Hf);
-    const u64 c2 = pk(ixc, iyc);
-    const u64 t2 = add2(c2, pk(kMagic, kMagic));                 // rounds to integer
-    f2 r = upk(add2(t2, pk(-kMagic, -kMagic)));                  // rint
-    const f2 tb = upk(t2);
-    int x0 = __float_as_int(tb.x) - 0x4B400000, y0 = __float_as_int(tb.y) - 0x4B400000;
-    if (r.x > ixc) { r.x = __fsub_rn(r.x, 1.0f); x0 -= 1; }      // rint -> floor
-    if (r.y > iyc) { r.y = __fsub_rn(r.y, 1.0f); y0 -= 1; }
-    f2 fr = upk(add2(c2, pk(-r.x, -r.y)));                       // (w, n) = pos - floor(pos)
-    if (!(fabsf(i.x) < INFINITY)) fr.x = __int_as_float(0x7fc00000);
-    if (!(fabsf(i.y) < INFINITY)) fr.y = __int_as_float(0x7fc00000);
-    const f2 one_m = upk(add2(pk(1.0f, 1.0f), pk(-fr.x, -fr.y)));   // (e, s) = 1 - (w, n)
-    const u64 ew = pk(one_m.x, fr.x);                            // (e, w)
-    const f2 top = upk(mul2(pk(one_m.y, one_m.y), ew));          // s*e, s*w
-    const f2 bot = upk(mul2(pk(fr.y, fr.y), ew));                // n*e, n*w
-    ViewCell c;
-    c.w00 = top.x; c.w01 = top.y; c.w10 = bot.x; c.w11 = bot.y;
-    if (p.border == 0) {
-        // Channels-last maps without a zero border.  A corner outside the map contributes
-        // 0 * weight in the reference; here the cell is moved inside the map, the weights of
-        // the corners that are really there move with their texels and every other slot gets
-        // weight * 0 (keeps NaN / inf weights poisonous, and the order of the non-zero
-        // terms of the blend is unchanged).  Needs W, H >= 2.
-        if (x0 < 0 || x0 > p.W - 2) {
-            const bool l_in = (x0 == p.W - 1), r_in = (x0 == -1);   // which real column survives
-            const float a0 = c.w00, a1 = c.w10;                     // weights of column x0
-            c.w00 = r_in ? c.w01 : __fmul_rn(c.w01, 0.0f);
-            c.w10 = r_in ? c.w11 : __fmul_rn(c.w11, 0.0f);
-            c.w01 = l_in ? a0 : __fmul_rn(a0, 0.0f);
-            c.w11 = l_in ? a1 : __fmul_rn(a1, 0.0f);
-            if (l_in) { c.w00 = __fmul_rn(c.w00, 0.0f); c.w10 = __fmul_rn(c.w10, 0.0f); }
-            if (r_in) { c.w01 = __fmul_rn(c.w01, 0.0f); c.w11 = __fmul_rn(c.w11, 0.0f); }
-            x0 = min(max(x0, 0), p.W - 2);
-        }
-        if (y0 < 0 || y0 > p.H - 2) {
-            const bool t_in = (y0 == p.H - 1), b_in = (y0 == -1);   // which real row survives
-            const float a0 = c.w00, a1 = c.w01;                     // weights of row y0
-            c.w00 = b_in ? c.w10 : __fmul_rn(c.w10, 0.0f);
-            c.w01 = b_in ? c.w11 : __fmul_rn(c.w11, 0.0f);
-            c.w10 = t_in ? a0 : __fmul_rn(a0, 0.0f);
-            c.w11 = t_in ? a1 : __fmul_rn(a1, 0.0f);
-            if (t_in) { c.w00 = __fmul_rn(c.w00, 0.0f); c.w01 = __fmul_rn(c.w01, 0.0f); }
-            if (b_in) { c.w10 = __fmul_rn(c.w10, 0.0f); c.w11 = __fmul_rn(c.w11, 0.0f); }
-            y0 = min(max(y0, 0), p.H - 2);
-        }
-    }
-    c.off = (unsigned)((y0 + p.border) * p.Wp + (x0 + p.border)) << lpb;
-    if (invalid) {                                   // :62 zero out non-valid points
-        c.off = 0;                                   // four border texels: exact +0
-        c.w00 = c.w01 = c.w10 = c.w11 = 0.0f;
-    }
-    return c;
-}
-
-__device__ __forceinline__ float ex2_approx(float x)   // bare MUFU.EX2; arguments here are <= 0
-{
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float rcp_approx(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float max_nan(float a, float b)
-{
-    float r;
-    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));   // torch.max propagates NaN
-    return r;
-}
-__device__ __forceinline__ float bf_lo(unsigned u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf_hi(unsigned u) { return __uint_as_float(u & 0xffff0000u); }
-
-// Blend of one channel pair: mul, then three FMAs (== ATen's contraction order)
-__device__ __forceinline__ u64 blend2(u64 t00, u64 t01, u64 t10, u64 t11, u64 w00, u64 w01, u64 w10, u64 w11)
-{
-    u64 acc = mul2(t00, w00);
-    acc = fma2(t01, w01, acc);
-    acc = fma2(t10, w10, acc);
-    return fma2(t11, w11, acc);
-}
-
-// NP channel pairs of one view from its four corner texels
-template <bool BF16>
-__device__ __forceinline__ void blend_texels(u64 *s, const uint4 &a, const uint4 &b, const uint4 &d,
-                                             const uint4 &e, const float4 &w)
-{
-    const u64 w00 = pk(w.x, w.x), w01 = pk(w.y, w.y), w10 = pk(w.z, w.z), w11 = pk(w.w, w.w);
-    if (BF16) {
-        const unsigned ua[4] = {a.x, a.y, a.z, a.w}, ub[4] = {b.x, b.y, b.z, b.w};
-        const unsigned ud[4] = {d.x, d.y, d.z, d.w}, ue[4] = {e.x, e.y, e.z, e.w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            s[i] = blend2(pk(bf_lo(ua[i]), bf_hi(ua[i])), pk(bf_lo(ub[i]), bf_hi(ub[i])),
-                          pk(bf_lo(ud[i]), bf_hi(ud[i])), pk(bf_lo(ue[i]), bf_hi(ue[i])), w00, w01, w10, w11);
-    } else {
-        s[0] = blend2(pk(__uint_as_float(a.x), __uint_as_float(a.y)), pk(__uint_as_float(b.x), __uint_as_float(b.y)),
-                      pk(__uint_as_float(d.x), __uint_as_float(d.y)), pk(__uint_as_float(e.x), __uint_as_float(e.y)),
-                      w00, w01, w10, w11);
-        s[1] = blend2(pk(__uint_as_float(a.z), __uint_as_float(a.w)), pk(__uint_as_float(b.z), __uint_as_float(b.w)),
-                      pk(__uint_as_float(d.z), __uint_as_float(d.w)), pk(__uint_as_float(e.z), __uint_as_float(e.w)),
-                      w00, w01, w10, w11);
-    }
-}
 
 // View fusion of one channel pair; views arrive in order, VMAX at a time.
 //   sum/mean: acc = ((s0 + s1) + s2) ...   (the reference's order)
@@ -683,11 +443,6 @@ selftest_division_kernel(float d, unsigned long long *mismatches)
     if (bad) atomicAdd(mismatches, bad);
 }
 
-static int pow2ceil(int v) { int r = 1; while (r < v) r <<= 1; return r; }
-static int ilog2_exact(int v) { int l = 0; while ((1 << l) < v) ++l; return (1 << l) == v ? l : -1; }
-
-// 16-byte channel vectors per pixel, padded to a power of two
-static int nchunks_of(int dtype, int C) { return pow2ceil(dtype == MVHMR_BF16 ? (C + 7) / 8 : (C + 3) / 4); }
 
 template <int VMAX, bool EXACT, bool CACHE, bool BF16, int LPB>
 static cudaError_t launch_method(int method, dim3 grid, size_t smem, cudaStream_t st, const UnprojParams &p)

@@ -458,6 +458,36 @@ def test_backward_matches_torch_autograd(method):
         assert float(fd.grad[:, 2].abs().max()) < float(fd.grad[:, 0].abs().max())
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 32, 24, 24, 12, False), (1, 3, 5, 9, 13, 7, False), (1, 11, 8, 16, 16, 6, False),
+                                   (2, 4, 16, 16, 20, 9, True), (1, 6, 24, 12, 12, 5, True), (1, 2, 136, 8, 8, 5, False)])
+@pytest.mark.parametrize("method", METHODS)
+def test_backward_fast_path_against_simple_kernel_and_autograd(shape, method):
+    """The packed / vector-red backward against (a) the thread-per-voxel kernel, (b) torch autograd
+    through the reference's op sequence; V > 8 exercises the re-sampling pass, C = 136 two channel
+    passes, odd shapes the ragged tiles."""
+    from multiviewhmr_b200 import autograd as ag
+    B, V, C, H, W, G, bf16 = shape
+    g = torch.Generator().manual_seed(B * 100 + V * 10 + C)
+    f = torch.randn(B, V, C, H, W, generator=g)
+    if bf16:
+        f = f.bfloat16().float()
+    P = syn.make_projections(B, V, H, W, behind_views=(V - 1,) if V > 2 else ())
+    cv = (torch.rand(B, G, G + 1, G + 2, 3, generator=g) - 0.5) * 2400.0
+    gout = torch.randn(B, C, G, G + 1, G + 2, generator=g)
+    fr = f.clone().requires_grad_(True)
+    torch_port.unprojection(fr, P, cv, method).backward(gout)
+    fd, Pd, cvd, gd = cuda(f, P, cv, gout)
+    if bf16:
+        fd = fd.bfloat16()
+    fast = ag.unprojection_backward(gd, fd, Pd, cvd, method)
+    simple = ag.unprojection_backward(gd, fd, Pd, cvd, method, simple=True)
+    assert fast.shape == f.shape and fast.dtype == torch.float32
+    assert rel_l2(fast.cpu().numpy(), fr.grad.numpy()) < 1e-5
+    assert rel_l2(fast.cpu().numpy(), simple.cpu().numpy()) < 1e-5
+    if V > 2 and method in ("sum", "mean"):      # views behind the camera receive (almost) no gradient
+        assert float(fast[:, V - 1].abs().max()) < float(fast[:, 0].abs().max())
+
+
 def test_backward_bf16_features_and_module_training_step():
     w = syn.Workload("t", B=1, V=4, C=8, H=16, W=16, G=8)
     f, P, cv, _ = syn.make_inputs(w, seed=13)
