@@ -371,6 +371,44 @@ def test_coord_volume_kernel_full_size_bit_exact():
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("n", [1, 3, 4, 5, 1023, 4099])
+def test_geometry_kernels_ragged_sizes_and_raw_abi(n):
+    """The streaming kernels take 4 points per thread with 16-byte accesses; point counts that are
+    not multiples of 4, grids with N % 4 != 0 and misaligned buffers take the scalar paths."""
+    L = _lib.load()
+    dev = torch.device(DEV)
+    g = np.random.default_rng(n)
+    pts = (g.normal(size=(n + 1, 3)) * 700).astype(np.float32)
+    rot = syn.rotation_matrix([0.3, -0.5, 0.8], 1.1).astype(np.float32)
+    P = syn.ring_projection(0, 1, 4, 96, 96, 2500.0).astype(np.float32)
+    dpts = torch.from_numpy(pts).to(dev)
+    for skip in (0, 1):                              # skip=1: a view that starts 12 bytes into the buffer
+        src = dpts.reshape(-1)[3 * skip:3 * skip + 3 * n]
+        ref_src = pts[skip:skip + n]
+        out = torch.empty(n + 1, 3, device=dev).reshape(-1)[3 * skip:3 * skip + 3 * n]
+        _lib.check(L.mvhmr_rotate_points(_lib.ptr(out), _lib.ptr(src), _lib.host3(rot.reshape(-1).tolist()), n,
+                                         _lib.stream_ptr(dev)))
+        assert np.array_equal(out.cpu().numpy().reshape(n, 3), oracle.rotate_points(ref_src, rot))
+        Pd = torch.from_numpy(P).to(dev)
+        for euclid in (0, 1):
+            o = torch.empty(n * (2 if euclid else 3) + 4, device=dev)[(4 * skip):]
+            _lib.check(L.mvhmr_project_points(_lib.ptr(o), _lib.ptr(Pd), _lib.ptr(src), n, euclid, _lib.stream_ptr(dev)))
+            got = o[: n * (2 if euclid else 3)].cpu().numpy().reshape(n, -1)
+            assert np.array_equal(got, oracle.project_points(P, ref_src, euclid=bool(euclid)), equal_nan=True)
+    # coord volumes on a grid whose voxel count is not a multiple of 4 (and one that is)
+    for G in ((3, 5, 7), (2, 6, 9), (4, 3, 8)):
+        B = 3
+        centers = (g.normal(size=(B, 3)) * 100).astype(np.float32)
+        rots = np.stack([syn.rotation_matrix([0, 1, 0], t) for t in (0.0, 0.7, 4.0)]).astype(np.float32)
+        out = torch.empty(B, *G, 3, device=dev)
+        cen, rt = torch.from_numpy(centers).to(dev), torch.from_numpy(rots).to(dev)
+        pos, step = [-1250.0, -1000.0, -700.0], [33.0, 41.5, 57.25]
+        _lib.check(L.mvhmr_build_coord_volumes(_lib.ptr(out), _lib.ptr(cen), _lib.ptr(rt), _lib.host3(pos), _lib.host3(step),
+                                               B, G[0], G[1], G[2], _lib.stream_ptr(dev)))
+        ref = oracle.build_coord_volumes(centers, rots, np.float32(pos), np.float32(step), G)
+        assert np.array_equal(out.cpu().numpy(), ref)
+
+
 @pytest.mark.parametrize("B,J,G", [(2, 17, (16, 16, 16)), (1, 3, (5, 7, 9)), (1, 70, (4, 8, 8)), (2, 1, (3, 3, 3)),
                                    (1, 2, (40, 40, 40))])
 def test_soft_argmax(B, J, G):
