@@ -367,7 +367,7 @@ unproject_kernel(const UnprojParams p)
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, int H, int W,
-            int nchunks, int Hp, int Wp)
+            int nchunks, int Hp, int Wp, int vec)
 {
     constexpr int CPT = BF16 ? 8 : 4;            // channels per 16-byte vector
     constexpr int CB = 64;                       // channels per tile
@@ -386,6 +386,61 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
     const int CP = nchunks * CPT;
     const int kn_all = (CB / CPT < nchunks) ? CB / CPT : nchunks;      // vectors per channel block (power of two)
     const int kshift = 31 - __clz(kn_all);
+    if (vec) {
+        // Fast path (rows are whole, aligned 16-byte groups): every lane has one 16-byte load per
+        // channel in flight, four channels per warp at a time; the four border pixels of the row are
+        // written separately.
+        constexpr int EPV = BF16 ? 8 : 4;                              // elements per 16-byte load
+        for (int e = threadIdx.x; e < 4 * nchunks; e += blockDim.x) {
+            const int pxl = e / nchunks;
+            dst_row[(size_t)(pxl < 2 ? pxl : W + pxl) * nchunks + (e - pxl * nchunks)] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        for (int xs = 0; xs < W; xs += XB) {
+            const int xn = min(XB, W - xs), nq = xn / EPV;
+            for (int cb = 0; cb < CP; cb += CB) {
+                const int cn = min(CB, CP - cb);
+#pragma unroll 4
+                for (int c = warp; c < cn; c += 8) {
+                    if (lane < nq) {
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                        if (cb + c < C) {
+                            const size_t src = ((size_t)(bv * C + cb + c) * H + y) * W + xs;
+                            v = BF16 ? __ldg(reinterpret_cast<const uint4 *>(static_cast<const unsigned short *>(feats) + src) + lane)
+                                     : __ldg(reinterpret_cast<const uint4 *>(static_cast<const float *>(feats) + src) + lane);
+                        }
+                        if (BF16) {
+                            unsigned short *t = tile_h + c * (XB + 2) + lane * 8;
+                            t[0] = (unsigned short)v.x; t[1] = (unsigned short)(v.x >> 16); t[2] = (unsigned short)v.y; t[3] = (unsigned short)(v.y >> 16);
+                            t[4] = (unsigned short)v.z; t[5] = (unsigned short)(v.z >> 16); t[6] = (unsigned short)v.w; t[7] = (unsigned short)(v.w >> 16);
+                        } else {
+                            float *t = tile_f + c * (XB + 1) + lane * 4;
+                            t[0] = __uint_as_float(v.x); t[1] = __uint_as_float(v.y); t[2] = __uint_as_float(v.z); t[3] = __uint_as_float(v.w);
+                        }
+                    }
+                }
+                __syncthreads();
+                const int kn = cn / CPT;
+                for (int e = threadIdx.x; e < (xn << kshift); e += blockDim.x) {
+                    const int j = e >> kshift, k = e & (kn_all - 1);
+                    if (k < kn) {
+                        uint4 v;
+                        if (BF16) {
+                            unsigned h[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) h[i] = tile_h[(k * 8 + i) * (XB + 2) + j];
+                            v = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+                        } else {
+                            v = make_uint4(__float_as_uint(tile_f[(k * 4 + 0) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 1) * (XB + 1) + j]),
+                                           __float_as_uint(tile_f[(k * 4 + 2) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 3) * (XB + 1) + j]));
+                        }
+                        dst_row[(size_t)(xs + kBorder + j) * nchunks + cb / CPT + k] = v;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        return;
+    }
     for (int x0 = -kBorder; x0 < W + kBorder; x0 += XB) {
         const int xn = min(XB, W + kBorder - x0);                      // padded pixels in this block
         for (int cb = 0; cb < CP; cb += CB) {
@@ -509,10 +564,13 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     if (rows > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: too many rows");
     const int cp = nchunks * (feat_dtype == MVHMR_BF16 ? 8 : 4);
     const int tile_rows = cp < 64 ? cp : 64;                       // CB in the kernel
+    // rows made of whole 16-byte groups at 16-byte aligned addresses take the vector-load path
+    const int epv = feat_dtype == MVHMR_BF16 ? 8 : 4;
+    const int vec = (W % epv == 0) && (((uintptr_t)feats & 15) == 0);
     if (feat_dtype == MVHMR_BF16)
-        pack_kernel<true><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 2) * 2, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
+        pack_kernel<true><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 2) * 2, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp, vec);
     else
-        pack_kernel<false><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 1) * 4, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp);
+        pack_kernel<false><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 1) * 4, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp, vec);
     return check_launch("pack_kernel");
 }
 
