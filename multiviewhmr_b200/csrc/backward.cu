@@ -145,7 +145,9 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool BF16, int METHOD>
+// ACC (sum / mean, fp32 maps, V <= 4): contributions of consecutive voxels of a run that fall into the same cell of
+// a view are summed in registers and leave as one set of reds when the cell changes.
+template <bool BF16, int METHOD, bool ACC>
 __global__ void __launch_bounds__(kBwdWarps * 32)
 unproject_backward_packed_kernel(const BwdParams q)
 {
@@ -225,6 +227,22 @@ unproject_backward_packed_kernel(const BwdParams q)
             blend_texels<BF16>(s, t00, t01, t10, t11, reinterpret_cast<const float4 *>(r)[v]);
         };
 
+        constexpr int VA = ACC ? 4 : 1;
+        float acc[VA][4][NCH];
+        unsigned apix[VA];
+#pragma unroll
+        for (int v = 0; v < VA; ++v) apix[v] = 0xffffffffu;
+        auto scatter = [&](int v, unsigned pix, const float (*val)[NCH]) {       // four corner lines of one cell
+            char *g0 = gbase + (size_t)v * q.gplane_bytes + ((size_t)pix << q.glpb);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                char *dst = g0 + ((k & 1) ? gpx : 0u) + ((k & 2) ? grow : 0u);
+#pragma unroll
+                for (int h = 0; h < NCH / 4; ++h)
+                    red_add_v4(reinterpret_cast<float *>(dst) + 4 * h, val[k][4 * h], val[k][4 * h + 1], val[k][4 * h + 2], val[k][4 * h + 3]);
+            }
+        };
+
         const unsigned char *rec = recs + (grp * steps) * rec_bytes + grp * 16;
         int zl = grp * steps;
         for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
@@ -286,9 +304,9 @@ unproject_backward_packed_kernel(const BwdParams q)
                 }
             }
             // pass 2: d out / d s_v, scatter
-            for (int v = 0; v < V; ++v) {
+            auto pass2 = [&](const int v) {
                 const float4 w = reinterpret_cast<const float4 *>(rec)[v];
-                if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f && w.w == 0.0f) continue;   // depth <= 0: no gradient (:62)
+                if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f && w.w == 0.0f) return;    // depth <= 0: no gradient (:62)
                 float gs[NCH];
                 if (!FWD) {
 #pragma unroll
@@ -322,19 +340,43 @@ unproject_backward_packed_kernel(const BwdParams q)
                 bool any = false;
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) any = any || (gs[c] != 0.0f);
-                if (!any) continue;
+                if (!any) return;
                 const unsigned o_pix = reinterpret_cast<const unsigned *>(rec + wbytes)[v];
-                char *g0 = gbase + (size_t)v * q.gplane_bytes + ((size_t)o_pix << q.glpb);
                 const float wk[4] = {w.x, w.y, w.z, w.w};
+                if (ACC) {
+                    const int va = ACC ? v : 0;
+                    if (o_pix != apix[va]) {
+                        if (apix[va] != 0xffffffffu) scatter(v, apix[va], acc[va]);
+                        apix[va] = o_pix;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    char *dst = g0 + ((k & 1) ? gpx : 0u) + ((k & 2) ? grow : 0u);
+                        for (int k = 0; k < 4; ++k)
 #pragma unroll
-                    for (int h = 0; h < NCH / 4; ++h)
-                        red_add_v4(reinterpret_cast<float *>(dst) + 4 * h, gs[4 * h] * wk[k], gs[4 * h + 1] * wk[k],
-                                   gs[4 * h + 2] * wk[k], gs[4 * h + 3] * wk[k]);
+                            for (int c = 0; c < NCH; ++c) acc[va][k][c] = gs[c] * wk[k];
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+#pragma unroll
+                            for (int c = 0; c < NCH; ++c) acc[va][k][c] = fmaf(gs[c], wk[k], acc[va][k][c]);
+                    }
+                } else {
+                    float val[4][NCH];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c) val[k][c] = gs[c] * wk[k];
+                    scatter(v, o_pix, val);
                 }
+            };
+            if (ACC) {
+#pragma unroll
+                for (int v = 0; v < VA; ++v) if (v < V) pass2(v);
+            } else {
+                for (int v = 0; v < V; ++v) pass2(v);
             }
+        }
+        if (ACC) {                                   // cells still open at the end of the run
+#pragma unroll
+            for (int v = 0; v < VA; ++v) if (apix[v] != 0xffffffffu) scatter(v, apix[v], acc[v]);
         }
         __syncwarp();
     }
@@ -409,12 +451,12 @@ extern "C" size_t mvhmr_unproject_backward_workspace_bytes(int feat_dtype, int B
     return n;
 }
 
-template <bool BF16>
+template <bool BF16, bool ACC>
 static void launch_bwd(int method, dim3 grid, size_t smem, cudaStream_t st, const BwdParams &q)
 {
 #define MVHMR_BWD(M)                                                                                          \
     {                                                                                                         \
-        auto kern = unproject_backward_packed_kernel<BF16, M>;                                                \
+        auto kern = unproject_backward_packed_kernel<BF16, M, ACC>;                                           \
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
         kern<<<grid, kBwdWarps * 32, smem, st>>>(q);                                                          \
     }
@@ -500,7 +542,9 @@ extern "C" int mvhmr_unproject_aggregate_backward_ws(const float *grad_out, cons
         const long long nblk = (tasks + kBwdWarps - 1) / kBwdWarps;
         if (nblk > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_backward: too many voxels");
         dim3 grid((unsigned)nblk, B);
-        if (bf) launch_bwd<true>(method, grid, smem, st, q); else launch_bwd<false>(method, grid, smem, st, q);
+        if (bf) launch_bwd<true, false>(method, grid, smem, st, q);
+        else if (V <= 4 && !fwd) launch_bwd<false, true>(method, grid, smem, st, q);   // max / softmax: the accumulators cost too many registers
+        else launch_bwd<false, false>(method, grid, smem, st, q);
         int rc = check_launch("unproject_backward_packed_kernel");
         if (rc != MVHMR_OK) return rc;
     }
