@@ -1,3 +1,4 @@
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scripts/micro/red_bench scripts/micro/red_bench.cu
 // Microbenchmark: throughput of red.global.add.f32 vs red.global.add.v4.f32 on L2-resident lines,
 // 8 lanes per 128-byte line (the packed-gradient scatter pattern of the backward kernel).
 #include <cstdio>
