@@ -265,18 +265,20 @@ unproject_backward_packed_kernel(const BwdParams q)
                 if (keep) {
 #pragma unroll
                     for (int v = 0; v < VREG; ++v) if (v < V) sample(rec, v, sreg[v]);
-                }
-                for (int v = 0; v < V; ++v) {
-                    u64 sv[NP];
-                    if (keep) {
+                    if (METHOD == MVHMR_SOFTMAX) {           // all views at hand: the max first, then one exp per sample
 #pragma unroll
-                        for (int u = 0; u < VREG; ++u) if (u == v) {
+                        for (int i = 0; i < NP; ++i) {
+                            f2 mx = upk(sreg[0][i]);
 #pragma unroll
-                            for (int i = 0; i < NP; ++i) sv[i] = sreg[u][i];
+                            for (int v = 1; v < VREG; ++v) if (v < V) {
+                                const f2 x = upk(sreg[v][i]);
+                                mx.x = fmaxf(mx.x, x.x); mx.y = fmaxf(mx.y, x.y);
+                            }
+                            m[2 * i] = mx.x; m[2 * i + 1] = mx.y;
                         }
-                    } else {
-                        sample(rec, v, sv);
                     }
+                }
+                auto stats = [&](const int v, const u64 *sv) {
 #pragma unroll
                     for (int i = 0; i < NP; ++i) {
                         const f2 x = upk(sv[i]);
@@ -287,24 +289,41 @@ unproject_backward_packed_kernel(const BwdParams q)
                             const float sc = xs[e];
                             if (METHOD == MVHMR_MAX) {
                                 if (v == 0 || sc > m[c] || (sc != sc && m[c] == m[c])) { m[c] = sc; arg[c] = v; }
+                            } else if (keep) {
+                                const float ev = ex2_approx((sc - m[c]) * kLog2e);
+                                S[c] += ev;
+                                o[c] = fmaf(sc, ev, o[c]);             // A = sum s * e
                             } else {                                   // online softmax statistics
                                 const float mn = (v == 0) ? sc : fmaxf(m[c], sc);
                                 const float scale = (v == 0) ? 0.0f : ex2_approx((m[c] - mn) * kLog2e);
                                 const float ev = ex2_approx((sc - mn) * kLog2e);
                                 S[c] = fmaf(S[c], scale, ev);
-                                o[c] = fmaf(o[c], scale, sc * ev);     // A = sum s * e
+                                o[c] = fmaf(o[c], scale, sc * ev);
                                 m[c] = mn;
                             }
                         }
                     }
+                };
+                if (keep) {
+#pragma unroll
+                    for (int v = 0; v < VREG; ++v) if (v < V) stats(v, sreg[v]);
+                } else {
+                    for (int v = 0; v < V; ++v) {
+                        u64 sv[NP];
+                        sample(rec, v, sv);
+                        stats(v, sv);
+                    }
                 }
                 if (METHOD == MVHMR_SOFTMAX) {
 #pragma unroll
-                    for (int c = 0; c < NCH; ++c) o[c] = __fdividef(o[c], S[c]);       // out = A / S
+                    for (int c = 0; c < NCH; ++c) {
+                        S[c] = rcp_approx(S[c]);                       // from here on S holds 1 / sum e
+                        o[c] *= S[c];                                  // out = A / S
+                    }
                 }
             }
             // pass 2: d out / d s_v, scatter
-            auto pass2 = [&](const int v) {
+            auto pass2 = [&](const int v, const u64 *kept) {
                 const float4 w = reinterpret_cast<const float4 *>(rec)[v];
                 if (w.x == 0.0f && w.y == 0.0f && w.z == 0.0f && w.w == 0.0f) return;    // depth <= 0: no gradient (:62)
                 float gs[NCH];
@@ -313,12 +332,9 @@ unproject_backward_packed_kernel(const BwdParams q)
                     for (int c = 0; c < NCH; ++c) gs[c] = (METHOD == MVHMR_MEAN) ? g[c] * inv_v : g[c];
                 } else {
                     u64 sv[NP];
-                    if (keep) {
+                    if (kept) {
 #pragma unroll
-                        for (int u = 0; u < VREG; ++u) if (u == v) {
-#pragma unroll
-                            for (int i = 0; i < NP; ++i) sv[i] = sreg[u][i];
-                        }
+                        for (int i = 0; i < NP; ++i) sv[i] = kept[i];
                     } else {
                         sample(rec, v, sv);
                     }
@@ -331,7 +347,7 @@ unproject_backward_packed_kernel(const BwdParams q)
                             const int c = 2 * i + e;
                             if (METHOD == MVHMR_MAX) gs[c] = (arg[c] == v) ? g[c] : 0.0f;
                             else {
-                                const float pv = __fdividef(ex2_approx((xs[e] - m[c]) * kLog2e), S[c]);
+                                const float pv = ex2_approx((xs[e] - m[c]) * kLog2e) * S[c];
                                 gs[c] = g[c] * (pv * (1.0f + xs[e] - o[c]));
                             }
                         }
@@ -369,9 +385,12 @@ unproject_backward_packed_kernel(const BwdParams q)
             };
             if (ACC) {
 #pragma unroll
-                for (int v = 0; v < VA; ++v) if (v < V) pass2(v);
+                for (int v = 0; v < VA; ++v) if (v < V) pass2(v, nullptr);
+            } else if (FWD && keep) {
+#pragma unroll
+                for (int v = 0; v < VREG; ++v) if (v < V) pass2(v, sreg[v]);
             } else {
-                for (int v = 0; v < V; ++v) pass2(v);
+                for (int v = 0; v < V; ++v) pass2(v, nullptr);
             }
         }
         if (ACC) {                                   // cells still open at the end of the run
