@@ -199,3 +199,28 @@ def test_dropin_registers_reference_module_names():
             if k in ("models", "utils") or k.startswith(("models.", "utils.")):
                 sys.modules.pop(k)
         sys.modules.update(saved)
+
+
+def test_batched_projections_equal_the_camera_loop():
+    """VolumeGenerator._projections: the batched float64 path (element-wise K scaling + per-camera
+    dgemm through np.matmul) must give the bits of the reference's per-camera loop."""
+    from multiviewhmr_b200 import aggregation as agg, multiview
+    rng = np.random.default_rng(7)
+    B, V = 5, 4
+    cams = [[multiview.Camera(np.linalg.qr(rng.normal(size=(3, 3)))[0], rng.normal(size=3) * 900 + [0, 0, 4000.0],
+                              [[1145.04 + rng.normal(), 0.0, 512.54 + rng.normal()], [0.0, 1143.78, 515.45 + rng.normal()], [0, 0, 1.0]])
+             for _ in range(B)] for _ in range(V)]
+    batch = {"cameras": cams}
+    vg = agg.VolumeGenerator.__new__(agg.VolumeGenerator)
+    for img, feat in (((384, 384), (96, 96)), ((1000, 1002), (7, 9)), ((224, 256), (56, 64))):
+        fast = agg.VolumeGenerator._projections(vg, batch, img, feat, V, B)
+        slow = agg.VolumeGenerator._projections(vg, batch, img, feat, V, B, batched=False)
+        assert fast.dtype == np.float32 and fast.shape == (B, V, 3, 4)
+        assert np.array_equal(fast, slow)
+    K0 = cams[0][0].K.copy()
+    agg.VolumeGenerator._projections(vg, batch, (384, 384), (96, 96), V, B)
+    assert np.array_equal(cams[0][0].K, K0)                       # the caller's cameras are not modified
+    # cameras that are not plain float64 take the loop
+    cams[1][2].K = cams[1][2].K.astype(np.float32)
+    assert np.array_equal(agg.VolumeGenerator._projections(vg, batch, (384, 384), (96, 96), V, B),
+                          agg.VolumeGenerator._projections(vg, batch, (384, 384), (96, 96), V, B, batched=False))
