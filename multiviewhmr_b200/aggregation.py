@@ -176,10 +176,48 @@ def _grid_buffer(centers, rotations, device):
     return _to_device_async(np.concatenate([centers, rotations]), device)
 
 
+class _PinnedRing:
+    """A few reusable pinned staging buffers per device for the small host arrays (projection
+    matrices, cuboid centres, rotations) that go to the GPU on every call.  `pin_memory()` per call
+    works too, but each growth of torch's pinned pool is a `cudaHostAlloc` — milliseconds, and it
+    synchronises the device."""
+    SLOTS, BYTES = 8, 1 << 16
+
+    def __init__(self):
+        self.buf = [torch.empty(self.BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.SLOTS)]
+        self.done = [None] * self.SLOTS
+        self.next = 0
+
+    def stage(self, array, device):
+        src = torch.from_numpy(np.ascontiguousarray(array))
+        nbytes = src.numel() * src.element_size()
+        if nbytes > self.BYTES:
+            return src.pin_memory().to(device, non_blocking=True)
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        if self.done[i] is not None:
+            self.done[i].synchronize()                    # the copy that last used this slot (8 calls ago)
+        host = self.buf[i][:nbytes].view(src.dtype).view(src.shape)
+        host.copy_(src)
+        out = host.to(device, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.done[i] = ev
+        return out
+
+
+_rings = {}
+
+
 def _to_device_async(array, device):
     """Small host array -> device through pinned staging, without blocking the host
     (a pageable copy would wait for everything queued on the stream before it)."""
-    return torch.from_numpy(np.ascontiguousarray(array)).pin_memory().to(device, non_blocking=True)
+    device = torch.device(device)
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ring = _rings.get(key)
+    if ring is None:
+        ring = _rings[key] = _PinnedRing()
+    return ring.stage(array, device)
 
 
 def soft_argmax_3d(volumes, coord_volumes):
@@ -340,20 +378,26 @@ class VolumeGenerator(nn.Module):
         return P
 
     def _squeeze_channels(self, features, batch_size, n_views):
-        """`:189-191` the 1x1 conv over all views.  Without autograd the same contraction runs as one
+        """`:189-191` the 1x1 conv over all views.  Without autograd the same contraction can run as a
         batched GEMM whose output is pixel-major, (B,V,H,W,C) — the layout the fused kernel gathers
-        in place (`MVHMR_LAYOUT_NHWC`), so neither a transposition nor the pack pass is paid."""
+        in place (`MVHMR_LAYOUT_NHWC`), so neither a transposition nor the pack pass is paid
+        (B8 V4 256->32 ch 96x96 on B200: 132 us against 212 + 20 us for cuDNN conv + pack in fp32, 73 against
+        87 + 20 us with TF32).  The GEMM obeys `torch.backends.cuda.matmul.allow_tf32`, the conv
+        `torch.backends.cudnn.allow_tf32`; the GEMM route is taken only when both flags agree, so the
+        precision the user asked for never changes."""
         conv = self.process_feature[0]
         Cin, H, W = features.shape[-3:]
         Cout = conv.out_channels
         pixel = Cout * features.element_size()
         needs_grad = torch.is_grad_enabled() and (features.requires_grad or conv.weight.requires_grad)
-        if (self.channels_last and not needs_grad and conv.bias is not None and features.dtype == conv.weight.dtype
+        same_precision = bool(torch.backends.cuda.matmul.allow_tf32) == bool(torch.backends.cudnn.allow_tf32)
+        if (self.channels_last and not needs_grad and same_precision and conv.bias is not None
+                and features.dtype == conv.weight.dtype
                 and pixel >= 16 and pixel & (pixel - 1) == 0 and H >= 2 and W >= 2):
             BV = batch_size * n_views
             x = features.reshape(BV, Cin, H * W).transpose(1, 2)                    # (BV, HW, Cin), a view
-            wt = conv.weight.detach().view(Cout, Cin).t().unsqueeze(0).expand(BV, Cin, Cout)
-            y = torch.baddbmm(conv.bias.detach().view(1, 1, Cout), x, wt)           # (BV, HW, Cout) contiguous
+            y = torch.matmul(x, conv.weight.detach().view(Cout, Cin).t())           # (BV, HW, Cout) contiguous
+            y += conv.bias.detach()
             return y.view(batch_size, n_views, H, W, Cout).permute(0, 1, 4, 2, 3)
         features = features.view(-1, *features.shape[2:])
         features = self.process_feature(features)
