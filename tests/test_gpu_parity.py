@@ -561,3 +561,90 @@ def test_exact_division_shortcuts_exhaustively(d):
     bad = torch.zeros(1, dtype=torch.int64, device=DEV)
     _lib.check(_lib.load().mvhmr_selftest_division(d, _lib.ptr(bad), _lib.stream_ptr(torch.device(DEV))))
     assert int(bad.item()) == 0
+
+
+def _guarded(nbytes, dev, fill=0x5A, guard=4096):
+    """A uint8 buffer of nbytes with guard bands on both sides (16-byte aligned payload)."""
+    total = torch.full((guard + nbytes + guard + 16,), fill, dtype=torch.uint8, device=dev)
+    return total, total[guard:guard + nbytes]
+
+
+def _guards_intact(total, nbytes, fill=0x5A, guard=4096):
+    return bool((total[:guard] == fill).all()) and bool((total[guard + nbytes:] == fill).all())
+
+
+@pytest.mark.parametrize("shape", [(2, 3, 5, 9, 13, (3, 5, 7), False), (1, 4, 32, 16, 16, (8, 8, 33), False),
+                                   (2, 8, 12, 10, 6, (5, 4, 9), True), (1, 2, 136, 4, 4, (2, 3, 5), False)])
+def test_no_write_outside_the_callers_buffers(shape):
+    """compute-sanitizer is not available on this pool: every output / workspace buffer of the raw C ABI
+    is placed between guard bands instead, which must come back untouched (forward with NCHW / packed /
+    channels-last input, soft-argmax, coord volume, both backward kernels)."""
+    B, V, C, H, W, G, bf16 = shape
+    L = _lib.load()
+    dev = torch.device(DEV)
+    st = _lib.stream_ptr(dev)
+    g = torch.Generator().manual_seed(C)
+    f = torch.randn(B, V, C, H, W, generator=g)
+    P = syn.make_projections(B, V, H, W)
+    cv = (torch.rand(B, *G, 3, generator=g) - 0.5) * 2600.0
+    fd, Pd, cvd = cuda(f, P, cv)
+    if bf16:
+        fd = fd.bfloat16()
+    dt = _lib.BF16 if bf16 else _lib.F32
+    N = G[0] * G[1] * G[2]
+    ref = agg.unprojection(fd, Pd, cvd, "softmax")
+    # forward, NCHW input: output + workspace guarded
+    ws_bytes = L.mvhmr_unproject_workspace_bytes(dt, _lib.LAYOUT_NCHW, B, V, C, H, W)
+    out_t, out_b = _guarded(B * C * N * 4, dev)
+    ws_t, ws_b = _guarded(ws_bytes, dev)
+    tail = (B, V, C, H, W, G[0], G[1], G[2], _lib.SOFTMAX, 0, B, 0, N, 0, N, 0)
+    _lib.check(L.mvhmr_unproject_aggregate(_lib.ptr(fd), dt, _lib.LAYOUT_NCHW, _lib.ptr(Pd), _lib.ptr(cvd), _lib.ptr(out_b),
+                                           *tail, _lib.ptr(ws_b), ws_bytes, st))
+    torch.cuda.synchronize()
+    assert _guards_intact(out_t, B * C * N * 4) and _guards_intact(ws_t, ws_bytes)
+    assert torch.equal(out_b.view(torch.float32).view(B, C, *G), ref)
+    # forward from the packed planes (no workspace) and, where eligible, channels-last in place
+    out_t.fill_(0x5A)
+    _lib.check(L.mvhmr_unproject_aggregate(_lib.ptr(ws_b), dt, _lib.LAYOUT_PACKED, _lib.ptr(Pd), _lib.ptr(cvd), _lib.ptr(out_b),
+                                           *tail, None, 0, st))
+    torch.cuda.synchronize()
+    assert _guards_intact(out_t, B * C * N * 4) and torch.equal(out_b.view(torch.float32).view(B, C, *G), ref)
+    pixel = C * fd.element_size()
+    if pixel >= 16 and pixel & (pixel - 1) == 0:
+        fcl = fd.permute(0, 1, 3, 4, 2).contiguous()
+        out_t.fill_(0x5A)
+        _lib.check(L.mvhmr_unproject_aggregate(_lib.ptr(fcl), dt, _lib.LAYOUT_NHWC, _lib.ptr(Pd), _lib.ptr(cvd), _lib.ptr(out_b),
+                                               *tail, None, 0, st))
+        torch.cuda.synchronize()
+        assert _guards_intact(out_t, B * C * N * 4) and torch.equal(out_b.view(torch.float32).view(B, C, *G), ref)
+    # soft-argmax: records workspace and the (B,C,3) result
+    sa_ws = L.mvhmr_soft_argmax3d_workspace_bytes(B, C, N)
+    saw_t, saw_b = _guarded(sa_ws, dev)
+    sao_t, sao_b = _guarded(B * C * 3 * 4, dev)
+    _lib.check(L.mvhmr_soft_argmax3d(_lib.ptr(ref), _lib.ptr(cvd), _lib.ptr(sao_b), B, C, N, _lib.ptr(saw_b), sa_ws, st))
+    torch.cuda.synchronize()
+    assert _guards_intact(saw_t, sa_ws) and _guards_intact(sao_t, B * C * 3 * 4)
+    # coord volume
+    cvo_t, cvo_b = _guarded(B * N * 3 * 4, dev)
+    cen = torch.zeros(B, 3, device=dev)
+    rot = torch.eye(3, device=dev).repeat(B, 1, 1).contiguous()
+    _lib.check(L.mvhmr_build_coord_volumes(_lib.ptr(cvo_b), _lib.ptr(cen), _lib.ptr(rot), _lib.host3([-1250.0] * 3), _lib.host3([40.0] * 3),
+                                           B, G[0], G[1], G[2], st))
+    torch.cuda.synchronize()
+    assert _guards_intact(cvo_t, B * N * 3 * 4)
+    # backward: fast path (gradient + workspace) and the simple kernel
+    gout = torch.randn(B, C, N, device=dev)
+    bws = L.mvhmr_unproject_backward_workspace_bytes(dt, B, V, C, H, W, _lib.SOFTMAX)
+    gw_t, gw_b = _guarded(bws, dev)
+    gf_t, gf_b = _guarded(B * V * C * H * W * 4, dev)
+    _lib.check(L.mvhmr_unproject_aggregate_backward_ws(_lib.ptr(gout), _lib.ptr(fd), dt, _lib.ptr(Pd), _lib.ptr(cvd), _lib.ptr(gf_b),
+                                                       B, V, C, H, W, N, _lib.SOFTMAX, _lib.ptr(gw_b), bws, st))
+    torch.cuda.synchronize()
+    assert _guards_intact(gw_t, bws) and _guards_intact(gf_t, B * V * C * H * W * 4)
+    fast = gf_b.view(torch.float32).clone()
+    gf_b.zero_()
+    _lib.check(L.mvhmr_unproject_aggregate_backward(_lib.ptr(gout), _lib.ptr(fd), dt, _lib.ptr(Pd), _lib.ptr(cvd), _lib.ptr(gf_b),
+                                                    B, V, C, H, W, N, _lib.SOFTMAX, st))
+    torch.cuda.synchronize()
+    assert _guards_intact(gf_t, B * V * C * H * W * 4)
+    assert rel_l2(fast.cpu().numpy(), gf_b.view(torch.float32).cpu().numpy()) < 1e-5
