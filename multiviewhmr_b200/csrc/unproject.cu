@@ -626,6 +626,10 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     if (lz == 0) {
         const int parts = (gz + lz_cap - 1) / lz_cap;               // smallest equal split of a z row
         lz = (gz + parts - 1) / parts;
+        // The uncached path (V > 4) has no z-run state to amortise: full segments whose stores are
+        // whole 128-byte lines are worth more than equal ones (cfg5, gz = 80: 32+32+16 is 11 % faster
+        // than 27+27+26).
+        if (V > 4 && gz > lz_cap) lz = lz_cap;
     }
     int off_tile, warp_smem;
     size_t smem;
@@ -709,7 +713,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned resident = (unsigned)sms * MVHMR_MINBLOCKS;       // one CTA (or MINBLOCKS) per SM, persistent
     p.ychunk = 1;                                                    // largest y sweep that still leaves >= 6 rounds
-    for (unsigned yc = 8; yc > 1; yc >>= 1)
+    for (unsigned yc = (V > 4 ? 2 : 8); yc > 1; yc >>= 1)            // the uncached path prefers short sweeps
         if ((unsigned)gy % yc == 0 && ntasks / yc >= 6ll * resident) { p.ychunk = yc; break; }
     if (const char *env = getenv("MVHMR_YCHUNK")) { const int v = atoi(env); if (v >= 1) p.ychunk = (unsigned)v; }   // tuning knob
     const unsigned nchunk = (unsigned)((ntasks + p.ychunk - 1) / p.ychunk);
