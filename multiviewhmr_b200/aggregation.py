@@ -12,6 +12,7 @@ All tensors must be CUDA tensors; the library behind `_lib` is the only
 implementation (no eager fallback).
 """
 import ctypes
+import threading
 import os
 
 import numpy as np
@@ -187,12 +188,17 @@ class _PinnedRing:
         self.buf = [torch.empty(self.BYTES, dtype=torch.uint8).pin_memory() for _ in range(self.SLOTS)]
         self.done = [None] * self.SLOTS
         self.next = 0
+        self.lock = threading.Lock()
 
     def stage(self, array, device):
         src = torch.from_numpy(np.ascontiguousarray(array))
         nbytes = src.numel() * src.element_size()
         if nbytes > self.BYTES:
             return src.pin_memory().to(device, non_blocking=True)
+        with self.lock:
+            return self._stage_locked(src, nbytes, device)
+
+    def _stage_locked(self, src, nbytes, device):
         i = self.next
         self.next = (i + 1) % self.SLOTS
         if self.done[i] is not None:
@@ -207,6 +213,7 @@ class _PinnedRing:
 
 
 _rings = {}
+_rings_lock = threading.Lock()
 
 
 def _to_device_async(array, device):
@@ -214,9 +221,10 @@ def _to_device_async(array, device):
     (a pageable copy would wait for everything queued on the stream before it)."""
     device = torch.device(device)
     key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
-    ring = _rings.get(key)
-    if ring is None:
-        ring = _rings[key] = _PinnedRing()
+    with _rings_lock:
+        ring = _rings.get(key)
+        if ring is None:
+            ring = _rings[key] = _PinnedRing()
     return ring.stage(array, device)
 
 
