@@ -204,6 +204,13 @@ size_t mvhmr_soft_argmax3d_workspace_bytes(int B, int J, long long N);
 int mvhmr_soft_argmax3d(const float *vol, const float *coord, float *out,
                         int B, int J, long long N, void *ws, size_t ws_bytes, void *stream);
 
+/* The same over the first J channels of a wider volume: sample b starts at
+ * vol + b * sample_stride floats (sample_stride >= J*N; e.g. C*N for the leading
+ * J joints of a (B,C,G,G,G) aggregate), so no contiguous copy is needed. */
+int mvhmr_soft_argmax3d_strided(const float *vol, const float *coord, float *out,
+                                int B, int J, long long N, long long sample_stride,
+                                void *ws, size_t ws_bytes, void *stream);
+
 /* Shard form.  partials: (B,J,S,5) with S = num_slices(n1-n0), over voxels
  * [n0,n1) of each sample; vol / coord are indexed with the FULL N. */
 int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord, float *partials,

@@ -245,14 +245,22 @@ def soft_argmax_3d(volumes, coord_volumes):
     B, J = volumes.shape[:2]
     N = int(np.prod(volumes.shape[2:]))
     L = _lib.load()
-    vol = volumes.detach().contiguous()
+    vol = volumes.detach()
+    # the leading J channels of a wider aggregate (`vol[:, :J]`) are read in place: only the
+    # sample stride differs from a contiguous (B,J,...) tensor
+    inner = vol[0] if B else vol
+    if B and inner.is_contiguous() and (B == 1 or vol.stride(0) >= J * N):
+        sample_stride = vol.stride(0) if B > 1 else J * N
+    else:
+        vol = vol.contiguous()
+        sample_stride = J * N
     coord = coord_volumes.detach().float().contiguous()
     out = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
     ws_bytes = L.mvhmr_soft_argmax3d_workspace_bytes(B, J, N)
     ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(L.mvhmr_soft_argmax3d(_lib.ptr(vol), _lib.ptr(coord), _lib.ptr(out), B, J, N,
-                                         _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+        _lib.check(L.mvhmr_soft_argmax3d_strided(_lib.ptr(vol), _lib.ptr(coord), _lib.ptr(out), B, J, N, sample_stride,
+                                                 _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
     return out
 
 

@@ -56,7 +56,8 @@ __device__ __forceinline__ Rec shfl_xor(const Rec &r, int mask)
 template <bool VEC>
 __global__ void __launch_bounds__(kSaBlock)
 soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restrict__ coord,
-                            float *__restrict__ partials, int J, int jchunk, long long N, long long n0, long long n1, int S)
+                            float *__restrict__ partials, int J, int jchunk, long long N, long long n0, long long n1, int S,
+                            long long bstride)
 {
     const int b = blockIdx.y;
     const int j0 = blockIdx.z * jchunk, j1 = min(J, j0 + jchunk);
@@ -95,7 +96,7 @@ soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restri
     }
 
     auto load_joint = [&](int j, float *x) {
-        const float *vp = vol + ((size_t)b * J + j) * N + base;
+        const float *vp = vol + (size_t)b * bstride + (size_t)j * N + base;
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
             const int v0 = (h * 32 + lane) * 4;
@@ -205,8 +206,8 @@ extern "C" size_t mvhmr_soft_argmax3d_workspace_bytes(int B, int J, long long N)
     return (size_t)B * J * mvhmr_soft_argmax3d_num_slices(N) * 5 * sizeof(float);
 }
 
-extern "C" int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord, float *partials,
-                                            int B, int J, long long N, long long n0, long long n1, void *stream)
+static int partials_impl(const float *vol, const float *coord, float *partials,
+                         int B, int J, long long N, long long n0, long long n1, long long bstride, void *stream)
 {
     if (B < 0 || J < 0 || N < 1 || n0 < 0 || n1 > N || n0 >= n1)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: bad shape B=%d J=%d N=%lld window [%lld,%lld)", B, J, N, n0, n1);
@@ -216,12 +217,20 @@ extern "C" int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord
     const int S = mvhmr_soft_argmax3d_num_slices(n1 - n0);
     const int nz = (J + kSaJointChunk - 1) / kSaJointChunk, jchunk = (J + nz - 1) / nz;
     dim3 grid((unsigned)((S + kSaWarps - 1) / kSaWarps), B, nz);
-    const bool vec = (N % 4 == 0) && (n0 % 4 == 0) && (((uintptr_t)vol & 15) == 0);
+    if (bstride < (long long)J * N)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: sample stride %lld smaller than J*N", bstride);
+    const bool vec = (N % 4 == 0) && (n0 % 4 == 0) && (bstride % 4 == 0) && (((uintptr_t)vol & 15) == 0);
     if (vec)
-        soft_argmax_partials_kernel<true><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S);
+        soft_argmax_partials_kernel<true><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S, bstride);
     else
-        soft_argmax_partials_kernel<false><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S);
+        soft_argmax_partials_kernel<false><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S, bstride);
     return check_launch("soft_argmax_partials_kernel");
+}
+
+extern "C" int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord, float *partials,
+                                            int B, int J, long long N, long long n0, long long n1, void *stream)
+{
+    return partials_impl(vol, coord, partials, B, J, N, n0, n1, (long long)J * N, stream);
 }
 
 extern "C" int mvhmr_soft_argmax3d_finalize(const float *partials, float *out, int B, int J, int S, void *stream)
@@ -237,10 +246,17 @@ extern "C" int mvhmr_soft_argmax3d_finalize(const float *partials, float *out, i
 extern "C" int mvhmr_soft_argmax3d(const float *vol, const float *coord, float *out,
                                    int B, int J, long long N, void *ws, size_t ws_bytes, void *stream)
 {
+    return mvhmr_soft_argmax3d_strided(vol, coord, out, B, J, N, (long long)J * N, ws, ws_bytes, stream);
+}
+
+extern "C" int mvhmr_soft_argmax3d_strided(const float *vol, const float *coord, float *out,
+                                           int B, int J, long long N, long long sample_stride,
+                                           void *ws, size_t ws_bytes, void *stream)
+{
     const size_t need = mvhmr_soft_argmax3d_workspace_bytes(B, J, N);
     if (B > 0 && J > 0 && (!ws || ws_bytes < need))
         return fail(MVHMR_ERR_WORKSPACE, "soft_argmax3d: workspace of %zu bytes required, got %zu", need, ws_bytes);
-    int rc = mvhmr_soft_argmax3d_partials(vol, coord, (float *)ws, B, J, N, 0, N, stream);
+    int rc = partials_impl(vol, coord, (float *)ws, B, J, N, 0, N, sample_stride, stream);
     if (rc != MVHMR_OK) return rc;
     return mvhmr_soft_argmax3d_finalize((const float *)ws, out, B, J, mvhmr_soft_argmax3d_num_slices(N), stream);
 }

@@ -16,6 +16,6 @@ out = torch.empty((w.B, w.C, w.G, w.G, w.G), device=dev)
 for _ in range(iters):
     agg.unprojection(fd, Pd, cvd, w.method, out=out)
     if w.joints:
-        agg.soft_argmax_3d(out[:, :w.joints].contiguous(), cvd)
+        agg.soft_argmax_3d(out[:, :w.joints], cvd)      # channel slice read in place
 torch.cuda.synchronize()
 print('done', float(out.sum()))

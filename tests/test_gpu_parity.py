@@ -429,6 +429,25 @@ def test_soft_argmax(B, J, G):
     assert np.abs(host - truth).max() <= 1e-5 * float(cv.abs().max())
 
 
+def test_soft_argmax_reads_a_channel_slice_in_place():
+    """`vol[:, :J]` of a wider aggregate (cfg3: 17 joints out of 32 channels) is not copied: the ABI takes
+    the sample stride."""
+    g = torch.Generator().manual_seed(2)
+    vol = (torch.randn(3, 8, 6, 5, 4, generator=g) * 4).to(DEV)
+    cv = ((torch.rand(3, 6, 5, 4, 3, generator=g) - 0.5) * 2000).to(DEV)
+    for J in (1, 3, 8):
+        sl = vol[:, :J]
+        assert sl.is_contiguous() == (J == 8)
+        assert torch.equal(agg.soft_argmax_3d(sl, cv), agg.soft_argmax_3d(sl.contiguous(), cv))
+    assert torch.equal(agg.soft_argmax_3d(vol[:1, 2:5], cv[:1]), agg.soft_argmax_3d(vol[:1, 2:5].contiguous(), cv[:1]))
+    # a slice that is not a leading-channel window is still correct (copied)
+    assert torch.equal(agg.soft_argmax_3d(vol[:, ::2], cv), agg.soft_argmax_3d(vol[:, ::2].contiguous(), cv))
+    L = _lib.load()
+    one = torch.zeros(4, device=DEV)
+    rc = L.mvhmr_soft_argmax3d_strided(_lib.ptr(vol), _lib.ptr(cv), _lib.ptr(one), 3, 8, 120, 100, _lib.ptr(vol), 1 << 20, None)
+    assert rc == _lib.ERR_INVALID_ARGUMENT and b"sample stride" in L.mvhmr_last_error()
+
+
 def test_soft_argmax_extreme_logits():
     vol = torch.full((1, 2, 4, 4, 4), -1e4)
     vol[0, 0, 1, 2, 3] = 80.0            # one-hot after softmax
