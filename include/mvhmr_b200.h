@@ -162,6 +162,14 @@ int mvhmr_unproject_aggregate_grid(const void *feats, int feat_dtype, int feat_l
                                    long long n_origin, long long n_extent,
                                    unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
 
+/* mvhmr_soft_argmax3d_strided with the voxel coordinates generated from `grid`
+ * (same arithmetic as mvhmr_build_coord_volumes, so the result has the same bits
+ * as building the coord volume first): with mvhmr_unproject_aggregate_grid no
+ * coordinate volume ever exists in device memory. */
+int mvhmr_soft_argmax3d_grid(const float *vol, const mvhmr_grid_t *grid, float *out,
+                             int B, int J, int gx, int gy, int gz, long long sample_stride,
+                             void *ws, size_t ws_bytes, void *stream);
+
 /* Backward of mvhmr_unproject_aggregate w.r.t. the feature maps (the gradient
  * torch autograd produces for models/aggregation.py:20-87; training goes through
  * this op, train.py:110).  grad_out (B,C,N) fp32; feats (B,V,C,H,W) NCHW fp32 or

@@ -42,6 +42,7 @@ SIGNATURES = {
     "mvhmr_soft_argmax3d_workspace_bytes": (_sz, [_i, _i, _ll]),
     "mvhmr_soft_argmax3d": (_i, [_vp, _vp, _vp, _i, _i, _ll, _vp, _sz, _vp]),
     "mvhmr_soft_argmax3d_strided": (_i, [_vp, _vp, _vp, _i, _i, _ll, _ll, _vp, _sz, _vp]),
+    "mvhmr_soft_argmax3d_grid": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp, _sz, _vp]),
     "mvhmr_soft_argmax3d_partials": (_i, [_vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp]),
     "mvhmr_soft_argmax3d_finalize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
 }

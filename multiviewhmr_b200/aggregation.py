@@ -245,15 +245,7 @@ def soft_argmax_3d(volumes, coord_volumes):
     B, J = volumes.shape[:2]
     N = int(np.prod(volumes.shape[2:]))
     L = _lib.load()
-    vol = volumes.detach()
-    # the leading J channels of a wider aggregate (`vol[:, :J]`) are read in place: only the
-    # sample stride differs from a contiguous (B,J,...) tensor
-    inner = vol[0] if B else vol
-    if B and inner.is_contiguous() and (B == 1 or vol.stride(0) >= J * N):
-        sample_stride = vol.stride(0) if B > 1 else J * N
-    else:
-        vol = vol.contiguous()
-        sample_stride = J * N
+    vol, sample_stride = _leading_channels_view(volumes)
     coord = coord_volumes.detach().float().contiguous()
     out = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
     ws_bytes = L.mvhmr_soft_argmax3d_workspace_bytes(B, J, N)
@@ -261,6 +253,45 @@ def soft_argmax_3d(volumes, coord_volumes):
     with torch.cuda.device(dev):
         _lib.check(L.mvhmr_soft_argmax3d_strided(_lib.ptr(vol), _lib.ptr(coord), _lib.ptr(out), B, J, N, sample_stride,
                                                  _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+    return out
+
+
+def _leading_channels_view(volumes):
+    """(tensor, sample_stride) such that `tensor` can be read in place as the leading J channels of
+    each sample; copies only when the layout is not a leading-channel window."""
+    B, J = volumes.shape[:2]
+    N = int(np.prod(volumes.shape[2:]))
+    vol = volumes.detach()
+    if B and vol[0].is_contiguous() and (B == 1 or vol.stride(0) >= J * N):
+        return vol, (vol.stride(0) if B > 1 else J * N)
+    return vol.contiguous(), J * N
+
+
+def soft_argmax_3d_grid(volumes, centers, rotations, cuboid_side):
+    """`soft_argmax_3d` over the cuboid grid of `models/aggregation.py:135-187` without a coord
+    volume: the voxel coordinates are generated inside the kernel from the per-sample centre and
+    rotation (host float32 arrays (B,3), (B,3,3)), with `build_coord_volumes`' arithmetic — the
+    result has the same bits as building the volume first.  With `unprojection_grid` in front no
+    coordinate volume exists in device memory at all."""
+    dev = _lib.require_cuda(volumes)
+    if volumes.dim() != 5 or volumes.dtype != torch.float32:
+        raise ValueError("expected float32 volumes (B,J,Gx,Gy,Gz), got %s %s" % (volumes.dtype, tuple(volumes.shape)))
+    B, J, gx, gy, gz = (int(v) for v in volumes.shape)
+    L = _lib.load()
+    vol, sample_stride = _leading_channels_view(volumes)
+    dev_buf = _grid_buffer(centers, rotations, dev)
+    grid = _lib.Grid()
+    grid.centers = dev_buf.data_ptr()
+    grid.rot = dev_buf.data_ptr() + B * 3 * 4
+    for k, g in enumerate((gx, gy, gz)):
+        grid.pos[k] = float(np.float32(0.0 - cuboid_side / 2))
+        grid.step[k] = float(np.float32(cuboid_side / (g - 1)))
+    out = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    ws_bytes = L.mvhmr_soft_argmax3d_workspace_bytes(B, J, gx * gy * gz)
+    ws = torch.empty(max(ws_bytes, 4), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(L.mvhmr_soft_argmax3d_grid(_lib.ptr(vol), ctypes.byref(grid), _lib.ptr(out), B, J, gx, gy, gz, sample_stride,
+                                              _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
     return out
 
 

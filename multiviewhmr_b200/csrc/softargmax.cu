@@ -52,12 +52,21 @@ __device__ __forceinline__ Rec shfl_xor(const Rec &r, int mask)
     return o;
 }
 
+// Cuboid grid of models/aggregation.py:135-187 for the GRID variant (coordinates generated, never read)
+struct SaGrid {
+    const float *centers, *rot;
+    float pos[3], step[3];
+    int gy, gz;
+};
+
 // VEC: N % 4 == 0 and n0 % 4 == 0 -> 16-byte loads of vol
-template <bool VEC>
+// GRID: the voxel coordinates come from the grid descriptor with coord_volume_kernel's arithmetic
+//       (bit-identical to reading a built coord volume) instead of from `coord`
+template <bool VEC, bool GRID>
 __global__ void __launch_bounds__(kSaBlock)
 soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restrict__ coord,
                             float *__restrict__ partials, int J, int jchunk, long long N, long long n0, long long n1, int S,
-                            long long bstride)
+                            long long bstride, const SaGrid g)
 {
     const int b = blockIdx.y;
     const int j0 = blockIdx.z * jchunk, j1 = min(J, j0 + jchunk);
@@ -69,7 +78,38 @@ soft_argmax_partials_kernel(const float *__restrict__ vol, const float *__restri
 
     // coordinates of this lane's 16 voxels (4 runs of 4 consecutive voxels), kept in registers
     float cx[16], cy[16], cz[16];
-    {
+    if (GRID) {
+        const float c0 = __ldg(g.centers + 3 * b), c1 = __ldg(g.centers + 3 * b + 1), c2 = __ldg(g.centers + 3 * b + 2);
+        float R[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) R[i] = __ldg(g.rot + 9 * b + i);
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const long long n = base + (h * 32 + lane) * 4;           // first voxel of this run of four
+            int ix, iy, iz;
+            if (N <= 0x7fffffffLL) {                                   // 32-bit index arithmetic
+                const unsigned t = (unsigned)n / (unsigned)g.gz;
+                iz = (int)((unsigned)n - t * (unsigned)g.gz);
+                ix = (int)(t / (unsigned)g.gy);
+                iy = (int)(t - (unsigned)ix * (unsigned)g.gy);
+            } else {
+                iz = (int)(n % g.gz);
+                const long long t = n / g.gz;
+                iy = (int)(t % g.gy); ix = (int)(t / g.gy);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float d0 = __fsub_rn(__fadd_rn(g.pos[0], __fmul_rn(g.step[0], (float)ix)), c0);
+                const float d1 = __fsub_rn(__fadd_rn(g.pos[1], __fmul_rn(g.step[1], (float)iy)), c1);
+                const float d2 = __fsub_rn(__fadd_rn(g.pos[2], __fmul_rn(g.step[2], (float)iz)), c2);
+                const bool in = (h * 32 + lane) * 4 + i < qn;
+                cx[4 * h + i] = in ? __fadd_rn(rot_row(R[0], R[1], R[2], d0, d1, d2), c0) : 0.0f;
+                cy[4 * h + i] = in ? __fadd_rn(rot_row(R[3], R[4], R[5], d0, d1, d2), c1) : 0.0f;
+                cz[4 * h + i] = in ? __fadd_rn(rot_row(R[6], R[7], R[8], d0, d1, d2), c2) : 0.0f;
+                if (++iz == g.gz) { iz = 0; if (++iy == g.gy) { iy = 0; ++ix; } }
+            }
+        }
+    } else {
         const float *cp = coord + ((size_t)b * N + base) * 3;
         const bool al = (((uintptr_t)cp) & 15) == 0;
 #pragma unroll
@@ -206,31 +246,36 @@ extern "C" size_t mvhmr_soft_argmax3d_workspace_bytes(int B, int J, long long N)
     return (size_t)B * J * mvhmr_soft_argmax3d_num_slices(N) * 5 * sizeof(float);
 }
 
-static int partials_impl(const float *vol, const float *coord, float *partials,
+static int partials_impl(const float *vol, const float *coord, const SaGrid *grid, float *partials,
                          int B, int J, long long N, long long n0, long long n1, long long bstride, void *stream)
 {
     if (B < 0 || J < 0 || N < 1 || n0 < 0 || n1 > N || n0 >= n1)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: bad shape B=%d J=%d N=%lld window [%lld,%lld)", B, J, N, n0, n1);
     if (B == 0 || J == 0) return MVHMR_OK;
     if (B > 65535) return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: B=%d exceeds 65535", B);
-    if (!vol || !coord || !partials) return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: null pointer");
+    if (!vol || (!coord && !grid) || !partials) return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: null pointer");
     const int S = mvhmr_soft_argmax3d_num_slices(n1 - n0);
     const int nz = (J + kSaJointChunk - 1) / kSaJointChunk, jchunk = (J + nz - 1) / nz;
-    dim3 grid((unsigned)((S + kSaWarps - 1) / kSaWarps), B, nz);
+    dim3 grid_dim((unsigned)((S + kSaWarps - 1) / kSaWarps), B, nz);
     if (bstride < (long long)J * N)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d: sample stride %lld smaller than J*N", bstride);
     const bool vec = (N % 4 == 0) && (n0 % 4 == 0) && (bstride % 4 == 0) && (((uintptr_t)vol & 15) == 0);
-    if (vec)
-        soft_argmax_partials_kernel<true><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S, bstride);
-    else
-        soft_argmax_partials_kernel<false><<<grid, kSaBlock, 0, (cudaStream_t)stream>>>(vol, coord, partials, J, jchunk, N, n0, n1, S, bstride);
+    const SaGrid none = {};
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grid) {
+        if (vec) soft_argmax_partials_kernel<true, true><<<grid_dim, kSaBlock, 0, st>>>(vol, nullptr, partials, J, jchunk, N, n0, n1, S, bstride, *grid);
+        else soft_argmax_partials_kernel<false, true><<<grid_dim, kSaBlock, 0, st>>>(vol, nullptr, partials, J, jchunk, N, n0, n1, S, bstride, *grid);
+    } else {
+        if (vec) soft_argmax_partials_kernel<true, false><<<grid_dim, kSaBlock, 0, st>>>(vol, coord, partials, J, jchunk, N, n0, n1, S, bstride, none);
+        else soft_argmax_partials_kernel<false, false><<<grid_dim, kSaBlock, 0, st>>>(vol, coord, partials, J, jchunk, N, n0, n1, S, bstride, none);
+    }
     return check_launch("soft_argmax_partials_kernel");
 }
 
 extern "C" int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord, float *partials,
                                             int B, int J, long long N, long long n0, long long n1, void *stream)
 {
-    return partials_impl(vol, coord, partials, B, J, N, n0, n1, (long long)J * N, stream);
+    return partials_impl(vol, coord, nullptr, partials, B, J, N, n0, n1, (long long)J * N, stream);
 }
 
 extern "C" int mvhmr_soft_argmax3d_finalize(const float *partials, float *out, int B, int J, int S, void *stream)
@@ -256,7 +301,28 @@ extern "C" int mvhmr_soft_argmax3d_strided(const float *vol, const float *coord,
     const size_t need = mvhmr_soft_argmax3d_workspace_bytes(B, J, N);
     if (B > 0 && J > 0 && (!ws || ws_bytes < need))
         return fail(MVHMR_ERR_WORKSPACE, "soft_argmax3d: workspace of %zu bytes required, got %zu", need, ws_bytes);
-    int rc = partials_impl(vol, coord, (float *)ws, B, J, N, 0, N, sample_stride, stream);
+    int rc = partials_impl(vol, coord, nullptr, (float *)ws, B, J, N, 0, N, sample_stride, stream);
+    if (rc != MVHMR_OK) return rc;
+    return mvhmr_soft_argmax3d_finalize((const float *)ws, out, B, J, mvhmr_soft_argmax3d_num_slices(N), stream);
+}
+
+extern "C" int mvhmr_soft_argmax3d_grid(const float *vol, const mvhmr_grid_t *grid, float *out,
+                                        int B, int J, int gx, int gy, int gz, long long sample_stride,
+                                        void *ws, size_t ws_bytes, void *stream)
+{
+    if (!grid || !grid->centers || !grid->rot)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d_grid: null grid descriptor / centers / rot");
+    if (gx < 1 || gy < 1 || gz < 1)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "soft_argmax3d_grid: bad grid (%d,%d,%d)", gx, gy, gz);
+    const long long N = (long long)gx * gy * gz;
+    const size_t need = mvhmr_soft_argmax3d_workspace_bytes(B, J, N);
+    if (B > 0 && J > 0 && (!ws || ws_bytes < need))
+        return fail(MVHMR_ERR_WORKSPACE, "soft_argmax3d: workspace of %zu bytes required, got %zu", need, ws_bytes);
+    SaGrid g;
+    g.centers = grid->centers; g.rot = grid->rot;
+    for (int k = 0; k < 3; ++k) { g.pos[k] = grid->pos[k]; g.step[k] = grid->step[k]; }
+    g.gy = gy; g.gz = gz;
+    int rc = partials_impl(vol, nullptr, &g, (float *)ws, B, J, N, 0, N, sample_stride, stream);
     if (rc != MVHMR_OK) return rc;
     return mvhmr_soft_argmax3d_finalize((const float *)ws, out, B, J, mvhmr_soft_argmax3d_num_slices(N), stream);
 }

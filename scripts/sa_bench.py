@@ -16,7 +16,22 @@ print('max abs err', (got.double() - ref).abs().max().item(), 'max|coord|', cv.a
 import pynvml
 pynvml.nvmlInit()
 h = pynvml.nvmlDeviceGetHandleByIndex(0)
-for fn, name in [(lambda v: agg.soft_argmax_3d_records(v, cv), 'partials'), (lambda v: agg.soft_argmax_3d(v, cv), 'total')]:
+import ctypes
+import numpy as np
+from multiviewhmr_b200 import _lib
+L = _lib.load()
+gbuf = torch.cat([torch.zeros(w.B * 3), torch.eye(3).repeat(w.B, 1, 1).reshape(-1)]).to(dev)     # centres, rotations
+grid = _lib.Grid(); grid.centers = gbuf.data_ptr(); grid.rot = gbuf.data_ptr() + w.B * 12
+for k in range(3):
+    grid.pos[k] = float(np.float32(-1250.0)); grid.step[k] = float(np.float32(2500.0 / (w.G - 1)))
+sa_out = torch.empty(w.B, w.joints, 3, device=dev)
+sa_ws = torch.empty(L.mvhmr_soft_argmax3d_workspace_bytes(w.B, w.joints, N), dtype=torch.uint8, device=dev)
+def grid_call(v):      # raw ABI: the python wrapper stages the descriptor through pinned memory, which a graph capture cannot contain
+    _lib.check(L.mvhmr_soft_argmax3d_grid(_lib.ptr(v), ctypes.byref(grid), _lib.ptr(sa_out), w.B, w.joints, w.G, w.G, w.G, w.joints * N,
+                                          _lib.ptr(sa_ws), sa_ws.numel(), _lib.stream_ptr(dev)))
+    return sa_out
+for fn, name in [(lambda v: agg.soft_argmax_3d_records(v, cv), 'partials'), (lambda v: agg.soft_argmax_3d(v, cv), 'total'),
+                 (grid_call, 'total, grid generated in-kernel')]:
   for ncall in (1, 6, 24):
     for i in range(6): fn(vols[i % 3])
     torch.cuda.synchronize()

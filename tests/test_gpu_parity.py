@@ -448,6 +448,18 @@ def test_soft_argmax_reads_a_channel_slice_in_place():
     assert rc == _lib.ERR_INVALID_ARGUMENT and b"sample stride" in L.mvhmr_last_error()
 
 
+def test_soft_argmax_over_the_generated_grid_has_the_bits_of_the_coord_volume_path():
+    g = np.random.default_rng(3)
+    for B, J, G in ((3, 5, 12), (2, 17, 33), (1, 2, 7)):
+        centers = (g.normal(size=(B, 3)) * 120).astype(np.float32)
+        rots = np.stack([syn.rotation_matrix([0, 0, 1], t) for t in g.uniform(0, 6.28, size=B)]).astype(np.float32)
+        vol = torch.from_numpy(g.normal(size=(B, J + 3, G, G, G)).astype(np.float32) * 4).to(DEV)
+        cv = agg.build_coord_volumes(centers, rots, G, 2500.0, torch.device(DEV))
+        ref = agg.soft_argmax_3d(vol[:, :J], cv)
+        got = agg.soft_argmax_3d_grid(vol[:, :J], centers, rots, 2500.0)
+        assert torch.equal(got, ref)
+
+
 def test_soft_argmax_extreme_logits():
     vol = torch.full((1, 2, 4, 4, 4), -1e4)
     vol[0, 0, 1, 2, 3] = 80.0            # one-hot after softmax
