@@ -347,9 +347,9 @@ def build_coord_volumes(centers, rotations, volume_size, cuboid_side, device):
     # cast to fp32 by torch when they meet the fp32 grid (`:156-158`)
     pos = np.float32(0.0 - cuboid_side / 2)
     step = np.float32(cuboid_side / (G - 1))
-    dev_buf = _to_device_async(np.concatenate([centers.reshape(B, 3), rotations.reshape(B, 9)], axis=1), device)
+    dev_buf = _grid_buffer(centers, rotations, device)            # B centres, then B rotations: two contiguous views
     out = torch.empty((B, G, G, G, 3), dtype=torch.float32, device=device)
-    cen, rot = dev_buf[:, :3].contiguous(), dev_buf[:, 3:].contiguous()
+    cen, rot = dev_buf[:B * 3], dev_buf[B * 3:]
     with torch.cuda.device(device):
         _lib.check(_lib.load().mvhmr_build_coord_volumes(
             _lib.ptr(out), _lib.ptr(cen), _lib.ptr(rot), _lib.host3([pos] * 3), _lib.host3([step] * 3),
