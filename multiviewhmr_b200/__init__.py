@@ -12,8 +12,8 @@ backed by hand-written CUDA kernels behind the C ABI in include/mvhmr_b200.h.
 module names.
 """
 from . import aggregation, multiview, volumetric  # noqa: F401
-from .aggregation import (VolumeGenerator, build_volume_generator, pack_features,  # noqa: F401
-                          soft_argmax_3d, unprojection)
+from .aggregation import (VolumeGenerator, build_coord_volumes, build_volume_generator, pack_features,  # noqa: F401
+                          soft_argmax_3d, soft_argmax_3d_grid, unprojection, unprojection_grid)
 
-__all__ = ["aggregation", "multiview", "volumetric", "unprojection", "VolumeGenerator",
-           "build_volume_generator", "soft_argmax_3d", "pack_features"]
+__all__ = ["aggregation", "multiview", "volumetric", "unprojection", "unprojection_grid", "VolumeGenerator",
+           "build_volume_generator", "build_coord_volumes", "soft_argmax_3d", "soft_argmax_3d_grid", "pack_features"]
