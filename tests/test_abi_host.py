@@ -224,3 +224,21 @@ def test_batched_projections_equal_the_camera_loop():
     cams[1][2].K = cams[1][2].K.astype(np.float32)
     assert np.array_equal(agg.VolumeGenerator._projections(vg, batch, (384, 384), (96, 96), V, B),
                           agg.VolumeGenerator._projections(vg, batch, (384, 384), (96, 96), V, B, batched=False))
+
+
+def test_header_is_c99_and_library_links_from_plain_c(built_lib, tmp_path):
+    """What a cgo / JNI / FFI binding sees: include/mvhmr_b200.h compiled as strict C99 by gcc and the
+    shared library linked into a C program (argument validation only, no device work)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    exe = str(tmp_path / "c_abi_smoke")
+    subprocess.run(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_abi", "c_abi_smoke.c"), "-o", exe,
+                    "-L", libdir, "-lmvhmr_b200", "-Wl,-rpath," + libdir], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "c abi ok" in out.stdout
