@@ -14,7 +14,10 @@ slowest rank's device time.
 Rank 0 prints ONE JSON line.  `value` is timed with inputs resident in HBM;
 `e2e` goes through the public Python API (`unprojection` -> ctypes -> C ABI)
 with pinned HOST buffers, host->device copies of every input and a
-device->host read of the step's metric inside the timed region.
+device->host read of the step's metric inside the timed region (median of
+three repetitions).  `extras.channels_last_in_place` is the same device-resident
+step when the feature maps arrive as (B,V,H,W,C) and are gathered in place
+(informative, not the headline).
 
 `--impl reference` times the reference's own CPU path (oracle/torch_port.py:
 the same ATen calls in the same order, all host threads) on a bounded sample of
