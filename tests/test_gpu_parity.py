@@ -680,3 +680,30 @@ def test_no_write_outside_the_callers_buffers(shape):
     torch.cuda.synchronize()
     assert _guards_intact(gf_t, B * V * C * H * W * 4)
     assert rel_l2(fast.cpu().numpy(), gf_b.view(torch.float32).cpu().numpy()) < 1e-5
+
+
+def test_voxel_indices_beyond_int32_through_a_compact_slab():
+    """Maximum sizes: a 2000 x 2000 x 1000 grid has 4e9 voxels (> 2^32 / 2).  The ABI lets a shard pass
+    only its slab of the coordinate / output buffers (n_origin, n_extent), so the 64-bit index path can be
+    exercised without 50 GB of memory: a ragged window near the end of the grid must give the bits of a
+    small call over the same coordinates."""
+    L = _lib.load()
+    dev = torch.device(DEV)
+    gx, gy, gz = 2000, 2000, 1000
+    n0 = (1999 * gy + 1000) * gz + 123
+    ext = 70001
+    assert n0 > 2 ** 31 and n0 + ext <= gx * gy * gz
+    B, V, C, H, W = 1, 2, 4, 8, 8
+    g = torch.Generator().manual_seed(11)
+    f = torch.randn(B, V, C, H, W, generator=g).to(dev)
+    P = syn.make_projections(B, V, H, W).to(dev)
+    cv = ((torch.rand(B, ext, 3, generator=g) - 0.5) * 2400.0).to(dev)
+    ref = agg.unprojection(f, P, cv.view(B, 1, 1, ext, 3), "softmax").view(B, C, ext)
+    out = torch.full((B, C, ext), float("nan"), device=dev)
+    ws_bytes = L.mvhmr_unproject_workspace_bytes(_lib.F32, _lib.LAYOUT_NCHW, B, V, C, H, W)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    _lib.check(L.mvhmr_unproject_aggregate(
+        _lib.ptr(f), _lib.F32, _lib.LAYOUT_NCHW, _lib.ptr(P), _lib.ptr(cv), _lib.ptr(out),
+        B, V, C, H, W, gx, gy, gz, _lib.SOFTMAX, 0, B, n0, n0 + ext, n0, ext, 0,
+        _lib.ptr(ws), ws_bytes, _lib.stream_ptr(dev)))
+    assert torch.equal(out, ref)
