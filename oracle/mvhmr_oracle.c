@@ -35,7 +35,7 @@
 #define ORC_MEAN 1
 #define ORC_MAX 2
 #define ORC_SOFTMAX 3
-#define ORC_MAX_VIEWS 64
+#define ORC_MAX_VIEWS 1024
 
 int orc_abi_version(void) { return 1; }
 

@@ -64,6 +64,10 @@ def test_argument_validation_needs_no_gpu(built_lib):
     rc = L.mvhmr_unproject_aggregate(*args, _lib.SUM, 0, 1, 0, 32 ** 3, 0, 32 ** 3, 65,
                                      one, 1 << 30, None)
     assert rc == _lib.ERR_INVALID_ARGUMENT and b"tile_hint" in L.mvhmr_last_error()
+    # more views than the per-warp voxel records can hold in shared memory: refused, not mis-launched
+    many = [one, _lib.F32, _lib.LAYOUT_NCHW, one, one, one, 1, 1024, 4, 8, 8, 4, 4, 4]
+    rc = L.mvhmr_unproject_aggregate(*many, _lib.SUM, 0, 1, 0, 64, 0, 64, 0, one, 1 << 30, None)
+    assert rc == _lib.ERR_INVALID_ARGUMENT and b"shared memory" in L.mvhmr_last_error()
     # channels-last input: gathered in place, so the pixel must be 16 * 2^k bytes and the map >= 2x2
     assert L.mvhmr_unproject_workspace_bytes(_lib.F32, _lib.LAYOUT_NHWC, 8, 4, 32, 96, 96) == 0
     nhwc = [one, _lib.F32, _lib.LAYOUT_NHWC, one, one, one, 1, 4, 17, 64, 64, 32, 32, 32]

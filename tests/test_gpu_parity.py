@@ -137,7 +137,9 @@ def test_cfg3_bf16_and_soft_argmax():
     (1, 4, 13, 8, 8, (7, 3, 16)), (2, 5, 8, 12, 20, (5, 5, 40)), (1, 8, 64, 10, 10, (3, 3, 32)),
     (1, 9, 4, 10, 10, (2, 2, 16)), (1, 17, 12, 10, 10, (2, 3, 8)), (3, 4, 32, 24, 24, (16, 16, 16)),
     # the reference's real operating point (cfg/baseline.yaml): 256 channels, 7x7 maps, 16^3 grid
-    (2, 4, 256, 7, 7, (16, 16, 16)), (1, 3, 200, 6, 5, (4, 4, 20)), (1, 2, 32, 16, 16, (3, 2, 80))])
+    (2, 4, 256, 7, 7, (16, 16, 16)), (1, 3, 200, 6, 5, (4, 4, 20)), (1, 2, 32, 16, 16, (3, 2, 80)),
+    # many views (the voxel records shrink the z segment down to one voxel), many channels (five passes), wide maps
+    (1, 64, 4, 8, 8, (3, 3, 9)), (1, 300, 4, 6, 6, (2, 2, 5)), (1, 2, 520, 4, 4, (2, 2, 6)), (1, 1, 4, 3, 700, (2, 3, 40))])
 @pytest.mark.parametrize("method", METHODS)
 def test_ragged_shapes(B, V, C, H, W, G, method):
     g = torch.Generator().manual_seed(B * 1000 + V * 100 + C)
