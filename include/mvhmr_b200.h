@@ -126,10 +126,13 @@ size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, i
  *   and written (pass 0,B,0,N for everything).  Slab and batch shards of one
  *   problem are bit-identical to the unsharded call.
  *   tile_hint: 0 = automatic; otherwise the number of consecutive z voxels
- *   (<= 64) one warp walks per task (tuning knob; results do not depend on it).
+ *   (<= 32) one warp walks per task (tuning knob; results do not depend on it).
  *   ws / ws_bytes: caller workspace (see mvhmr_unproject_workspace_bytes).
  * gx,gy,gz: volume shape; used only to cut the volume into z runs, any
- * factorisation with gx*gy*gz == N is legal. */
+ * factorisation with gx*gy*gz == N is legal.
+ * Limits: the padded maps of one sample stay below 4 GiB; V up to about 650
+ * (the per-voxel records of all views must fit the shared memory of a warp
+ * task: larger V returns MVHMR_ERR_INVALID_ARGUMENT); any C, H, W >= 1. */
 int mvhmr_unproject_aggregate(const void *feats, int feat_dtype, int feat_layout,
                               const float *proj, const float *coord, float *out,
                               int B, int V, int C, int H, int W,
