@@ -401,27 +401,33 @@ unproject_backward_packed_kernel(const BwdParams q)
     }
 }
 
-// pixel-major fp32 gradient planes (with border) -> (B*V, C, H, W).  One CTA per map row.
+// pixel-major fp32 gradient planes (with border) -> (B*V, C, H, W).  One CTA per map row; the pixel
+// vectors are read as 16-byte loads (CG is a multiple of 4), transposed through shared memory and
+// written as coalesced rows, one warp per channel.  No integer division per element.
 __global__ void __launch_bounds__(256)
 unpack_grad_kernel(const float *__restrict__ gpacked, float *__restrict__ gfeat, int C, int H, int W, int CG, int Wp, int Hp)
 {
     extern __shared__ float unpack_tile[];           // [min(CG,64)][XB+1]
     constexpr int XB = 128, CB = 64;
     const int bv = blockIdx.x / H, y = blockIdx.x % H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *src_row = gpacked + ((size_t)(bv * Hp + y + kBorder) * Wp + kBorder) * CG;
     for (int x0 = 0; x0 < W; x0 += XB) {
         const int xn = min(XB, W - x0);
         for (int cb = 0; cb < C; cb += CB) {
-            const int cn = min(CB, CG - cb);
-            for (int e = threadIdx.x; e < xn * cn; e += blockDim.x) {
-                const int j = e / cn, c = e - j * cn;
-                unpack_tile[c * (XB + 1) + j] = __ldg(src_row + (size_t)(x0 + j) * CG + cb + c);
+            const int cn = min(CB, CG - cb);             // a power of two >= 4
+            const int qshift = 31 - __clz(cn >> 2);      // log2(16-byte vectors per pixel in this block)
+            for (int e = threadIdx.x; e < (xn << qshift); e += blockDim.x) {
+                const int j = e >> qshift, q = e & ((cn >> 2) - 1);
+                const float4 v = __ldcs(reinterpret_cast<const float4 *>(src_row + (size_t)(x0 + j) * CG + cb) + q);
+                float *t = unpack_tile + (4 * q) * (XB + 1) + j;
+                t[0] = v.x; t[XB + 1] = v.y; t[2 * (XB + 1)] = v.z; t[3 * (XB + 1)] = v.w;
             }
             __syncthreads();
             const int cw = min(cn, C - cb);
-            for (int e = threadIdx.x; e < cw * xn; e += blockDim.x) {
-                const int c = e / xn, j = e - c * xn;
-                gfeat[((size_t)(bv * C + cb + c) * H + y) * W + x0 + j] = unpack_tile[c * (XB + 1) + j];
+            for (int c = warp; c < cw; c += 8) {
+                float *dst = gfeat + ((size_t)(bv * C + cb + c) * H + y) * W + x0;
+                for (int j = lane; j < xn; j += 32) dst[j] = unpack_tile[c * (XB + 1) + j];
             }
             __syncthreads();
         }
