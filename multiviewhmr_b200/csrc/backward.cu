@@ -147,8 +147,13 @@ __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, 
 
 // ACC (sum / mean, fp32 maps, V <= 4): contributions of consecutive voxels of a run that fall into the same cell of
 // a view are summed in registers and leave as one set of reds when the cell changes.
+#ifndef MVHMR_BWD_MINBLOCKS
+#define MVHMR_BWD_MINBLOCKS 3
+#endif
+// max / softmax re-sample the maps: three CTAs per SM (<= 80 registers, a few spilled words) hide that
+// latency better than two with everything in registers (cfg2: max 921 -> 841 us, softmax 1064 -> 1020 us)
 template <bool BF16, int METHOD, bool ACC>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32, (METHOD == MVHMR_MAX || METHOD == MVHMR_SOFTMAX) ? MVHMR_BWD_MINBLOCKS : 2)
 unproject_backward_packed_kernel(const BwdParams q)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
