@@ -1,28 +1,34 @@
 #!/usr/bin/env python
 """Benchmark of the volumetric-aggregation hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg5] [--impl reference]
 
-A step = one pass of the hot path (feature packing + fused unproject+aggregate)
-over one batch of synthetic input.  At N=1 the workload is BASELINE.json's
-configs[1] (cfg2: B8 V4 C32 96x96 -> 64^3, softmax fusion, fp32).  For N>1 the
-driver launches this file under torchrun, one rank per GPU; every rank owns its
-own batch of the same shape (batch sharding, no collective in the data path,
-"weak" scaling) and the reported value is the units of all ranks over the
-slowest rank's device time.
+Workload.  BASELINE.json quotes its metric "at 1/2/4/8 B200" on configs[4], the
+scaling sweep (cfg5: B64 V8 C32 96x96 -> 80^3, softmax fusion, fp32), which fits
+one GPU — so cfg5 is the headline at every N.  A step = one pass of the hot path
+(feature packing + fused unproject+aggregate) over this rank's share of the
+batch.  For N>1 the driver launches this file under torchrun, one rank per GPU;
+the B*Gx x-planes of the batch are cut with `sharding.shard_windows` (whole
+samples when N divides B — the reference's DDP batch split, train.py:166-168 —
+x-slabs otherwise), no collective in the data path, STRONG scaling: the total
+work is fixed and `value` is all ranks' units over the slowest rank's device time.
 
-Rank 0 prints ONE JSON line.  `value` is timed with inputs resident in HBM;
-`e2e` goes through the public Python API (`unprojection` -> ctypes -> C ABI)
-with pinned HOST buffers, host->device copies of every input and a
-device->host read of the step's metric inside the timed region (median of
-three repetitions).  `extras.channels_last_in_place` is the same device-resident
-step when the feature maps arrive as (B,V,H,W,C) and are gathered in place
-(informative, not the headline).
+Rank 0 prints ONE JSON line.
+  value      device-resident (inputs already in HBM), CUDA events, max over ranks
+  roofline   the fused kernel alone, CUDA events around its launches in the timed loop
+  e2e        the same step through the public Python API with pinned HOST inputs: H2D of the
+             feature maps / projections / coordinate volumes, pack + fused kernel, and the
+             D2H of the FULL aggregated volume (B,C,G,G,G) into pinned host memory, all
+             inside the timed region (three streams, double-buffered).  `e2e.consumer_on_gpu`
+             is the variant whose consumer stays on the GPU (soft-argmax -> (B,C,3) to host).
+  configs    (N=1 only) every BASELINE config cfg1..cfg5 device-resident: ms, Gvcv/s and the
+             fraction of the HBM roofline of the fused kernel (cfg3 also its soft-argmax)
+  extras.backward (N=1 only) the gradient kernels at cfg2 and cfg4 with their roofline
 
-`--impl reference` times the reference's own CPU path (oracle/torch_port.py:
-the same ATen calls in the same order, all host threads) on a bounded sample of
-the same workload.  That is the only place besides `cpu_baseline` where this
-file executes anything under oracle/.
+`--impl reference` times the reference's own CPU path (oracle/torch_port.py: the same
+ATen calls in the same order, all host threads) on a bounded sample of the same
+workload.  That is the only place besides `cpu_baseline` where this file executes
+anything under oracle/.
 """
 import argparse
 import json
@@ -37,11 +43,12 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-from multiviewhmr_b200 import synthetic as syn  # noqa: E402
+from multiviewhmr_b200 import sharding, synthetic as syn  # noqa: E402
 
 METRIC = "Gvoxel-ch-views/s fused unproject+aggregate"
 UNIT = "Gvcv/s"
 L2_BYTES = 126 * 1024 * 1024
+HEADLINE = "cfg5"
 
 
 def measured_peak():
@@ -116,6 +123,10 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(s)}
 
 
+def sub_workload(w, B, name=None):
+    return syn.Workload(name or w.name, B, w.V, w.C, w.H, w.W, w.G, w.method, w.dtype, w.joints, w.cuboid_side)
+
+
 def cpu_reference_sample(w, steps, warmup, n_samples=2):
     """Time the torch port of the reference on the host cores: the first
     `n_samples` samples of the workload's batch (the reference loops per sample,
@@ -123,7 +134,8 @@ def cpu_reference_sample(w, steps, warmup, n_samples=2):
     from oracle import torch_port          # CPU baseline leg: the one allowed use of oracle/
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    f, P, cv, _ = syn.make_inputs(syn.Workload("s", n_samples, w.V, w.C, w.H, w.W, w.G, w.method, w.dtype))
+    n_samples = min(n_samples, w.B)
+    f, P, cv, _ = syn.make_inputs(sub_workload(w, n_samples, "s"))
     for _ in range(warmup):
         torch_port.unprojection(f, P, cv, w.method)
     times = []
@@ -137,6 +149,18 @@ def cpu_reference_sample(w, steps, warmup, n_samples=2):
         n_samples, w.B, w.name, cores)
 
 
+def config_of(w, world):
+    """Identical in both arms (the driver compares the two lines' `config`)."""
+    return {"workload": describe(w), "global_batch": w.B,
+            "parallelism": "shard_windows over %d rank(s): batch split%s, no collective in the data path"
+                           % (world, "" if w.B % world == 0 else " + x-slabs")}
+
+
+def describe(w):
+    return "%s: B%d V%d C%d %dx%d -> %d^3, %s fusion, %s features" % (
+        w.name, w.B, w.V, w.C, w.H, w.W, w.G, w.method, w.dtype)
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -146,8 +170,9 @@ def run_reference(args, w):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": describe(w), "sample": sample},
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_of(w, args.gpus),
+        "notes": {"sample": sample, "arm": "the reference's torch CPU path on rank 0's host cores; no GPU work"},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -155,19 +180,238 @@ def run_reference(args, w):
     print(json.dumps(line), flush=True)
 
 
-def describe(w):
-    return "%s: B%d V%d C%d %dx%d -> %d^3, %s fusion, %s features" % (
-        w.name, w.B, w.V, w.C, w.H, w.W, w.G, w.method, w.dtype)
+class RankShare:
+    """This rank's windows of workload `w` and synthetic inputs for exactly the samples they touch."""
+
+    def __init__(self, w, rank, world, dev, n_sets_min=1):
+        self.w, self.dev = w, dev
+        self.windows = sharding.shard_windows(w.B, w.G, rank, world)
+        self.b_lo = min([x.b0 for x in self.windows], default=0)
+        self.b_hi = max([x.b1 for x in self.windows], default=0)
+        self.nb = self.b_hi - self.b_lo
+        self.units = sum(x.units() for x in self.windows) * w.G * w.G * w.C * w.V     # voxel-channel-views of this rank
+        e = 2 if w.dtype == "bf16" else 4
+        self.in_bytes = self.nb * (w.V * w.C * w.H * w.W * e + w.G ** 3 * 12 + w.V * 48)
+        self.out_bytes = self.nb * w.C * w.G ** 3 * 4
+        # rotating input sets: more input bytes in flight than the 126 MB L2 holds
+        self.n_sets = max(n_sets_min, min(8, -(-2 * L2_BYTES // max(self.in_bytes, 1)))) if self.nb else 0
+        lw = sub_workload(w, self.nb)
+        self.host_sets, self.dev_sets = [], []
+        for i in range(self.n_sets):
+            f, P, cv, centers = syn.make_inputs(lw, seed=1234 + 1000 * i + self.b_lo, b_offset=self.b_lo)
+            if w.dtype == "bf16":
+                f = f.bfloat16()
+            self.host_sets.append((f, P, centers.numpy()))
+            self.dev_sets.append(tuple(t.to(dev) for t in (f, P, cv)))
+        self.outs = [torch.empty((self.nb, w.C, w.G, w.G, w.G), dtype=torch.float32, device=dev) for _ in range(2)]
+
+    def local_windows(self):
+        gy = gz = self.w.G
+        for x in self.windows:
+            n0, n1 = x.voxels(gy, gz)
+            yield (x.b0 - self.b_lo, x.b1 - self.b_lo, n0, n1)
+
+    def launches_per_step(self):
+        return 1 + len(self.windows)            # pack_kernel + one fused kernel per window
+
+    def step(self, agg, i, out=None, inputs=None):
+        """pack + fused kernel(s) over this rank's windows; returns the output buffer."""
+        f, P, cv = inputs if inputs is not None else self.dev_sets[i % self.n_sets]
+        out = self.outs[i % 2] if out is None else out
+        packed = agg.pack_features(f)
+        for win in self.local_windows():
+            agg.unprojection(f, P, cv, self.w.method, window=win, out=out, packed=packed)
+        return out
+
+
+def time_device_resident(agg, share, steps, warmup, stream, barrier, sampler=None):
+    """K steps of (pack + fused kernel); returns (ms/step over the whole loop, fused-kernel ms/step)."""
+    if share.nb == 0:
+        barrier(); barrier()
+        return 0.0, 0.0
+    kern_ev = []
+    for i in range(warmup):
+        share.step(agg, i)
+    barrier()
+
+    def loop():
+        for i in range(steps):
+            f, P, cv = share.dev_sets[i % share.n_sets]
+            out = share.outs[i % 2]
+            packed = agg.pack_features(f)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for win in share.local_windows():
+                agg.unprojection(f, P, cv, share.w.method, window=win, out=out, packed=packed)
+            e1.record(stream)
+            kern_ev.append((e0, e1))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler is not None:
+        with sampler:
+            t0.record(stream); loop(); t1.record(stream)
+            barrier()
+    else:
+        t0.record(stream); loop(); t1.record(stream)
+        barrier()
+    return t0.elapsed_time(t1) / steps, sum(a.elapsed_time(b) for a, b in kern_ev) / len(kern_ev)
+
+
+def time_e2e(agg, share, steps, stream, barrier, dev, full_d2h, sampler):
+    """pinned host inputs -> H2D -> pack + fused kernel -> D2H of the result, three streams,
+    double-buffered; every copy and kernel of all steps is inside the timed region.
+    Returns (median ms per step of 3 repetitions, the repetitions, h2d bytes, d2h bytes)."""
+    w = share.w
+    if share.nb == 0:
+        for _ in range(5):
+            barrier()
+        return 0.0, [0.0, 0.0, 0.0], 0, 0
+    # Host inputs of a step, as in VolumeGenerator.forward (models/aggregation.py:119-193): feature maps,
+    # projection matrices and the per-sample cuboid centre / rotation; the coordinate volume itself is
+    # built on the device (the reference builds it there too, :150-187).
+    host_sets = [tuple(t.pin_memory() for t in hs[:2]) for hs in share.host_sets]
+    centers_sets = [hs[2] for hs in share.host_sets]
+    rots_np = np.stack([np.eye(3, dtype=np.float32)] * share.nb)
+    h2d = sum(t.numel() * t.element_size() for t in host_sets[0]) + share.nb * 12 * 4
+    if full_d2h:
+        host_out = [torch.empty((share.nb, w.C, w.G, w.G, w.G), dtype=torch.float32).pin_memory() for _ in range(2)]
+    else:
+        host_out = [torch.empty((share.nb, w.C, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
+    d2h = host_out[0].numel() * 4
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    dev_in = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0]) for _ in range(2)]
+    grid_in = [None, None]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    computed = [torch.cuda.Event() for _ in range(2)]
+    drained = [torch.cuda.Event() for _ in range(2)]
+
+    def stage(i):
+        slot = i % 2
+        with torch.cuda.stream(copy_in):
+            copy_in.wait_event(consumed[slot])                # the slot's previous user is done
+            for d, h in zip(dev_in[slot], host_sets[i % len(host_sets)]):
+                d.copy_(h, non_blocking=True)
+            grid_in[slot] = agg.build_coord_volumes(centers_sets[i % len(host_sets)], rots_np, w.G, w.cuboid_side, dev)
+            copied[slot].record(copy_in)
+
+    def run(n):
+        for ev in consumed + drained:
+            ev.record(stream)
+        stage(0)
+        for i in range(n):
+            slot = i % 2
+            if i + 1 < n:
+                stage(i + 1)
+            stream.wait_event(copied[slot])
+            stream.wait_event(drained[slot])                  # the output buffer's previous D2H is done
+            cv = grid_in[slot]
+            cv.record_stream(stream)
+            vol = share.step(agg, i, out=share.outs[slot], inputs=dev_in[slot] + (cv,))
+            if full_d2h:
+                computed[slot].record(stream)
+                consumed[slot].record(stream)
+                with torch.cuda.stream(copy_out):
+                    copy_out.wait_event(computed[slot])
+                    host_out[slot].copy_(vol, non_blocking=True)
+                    drained[slot].record(copy_out)
+            else:
+                joints = agg.soft_argmax_3d(vol, cv)                  # the consumer stays on the GPU
+                host_out[slot].copy_(joints, non_blocking=True)
+                consumed[slot].record(stream)
+                drained[slot].record(stream)
+        stream.wait_stream(copy_out)
+
+    run(2)
+    barrier()
+    reps = []
+    with sampler:
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run(steps)
+            e1.record(stream)
+            barrier()
+            reps.append(e0.elapsed_time(e1) / steps)
+    del host_out, dev_in, host_sets
+    return sorted(reps)[1], reps, h2d, d2h
+
+
+def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_entry):
+    """cfg1..cfg5 device-resident on one GPU: pack + fused kernel (cfg3: + soft-argmax)."""
+    block = {}
+    for name in sorted(syn.CONFIGS):
+        if name == headline_name:
+            block[name] = headline_entry
+            continue
+        w = syn.CONFIGS[name]
+        share = RankShare(w, 0, 1, dev)
+        steps = 60 if w.vcv < 1e9 else 20
+        ms, kms = time_device_resident(agg, share, steps, 3, stream, barrier)
+        alg = w.algorithmic_bytes()
+        entry = {"workload": describe(w), "ms_per_step": ms, "kernel_ms": kms, "value": w.vcv / (ms * 1e-3) / 1e9, "unit": UNIT,
+                 "algorithmic_bytes": alg, "roofline_frac": alg / (kms * 1e-3) / 1e9 / peak,
+                 "step_frac": alg / (ms * 1e-3) / 1e9 / peak, "steps": steps}
+        if w.joints:
+            f, P, cv = share.dev_sets[0]
+            vol = share.step(agg, 0)
+            for _ in range(3):
+                agg.soft_argmax_3d(vol[:, :w.joints], cv)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                agg.soft_argmax_3d(share.outs[i % 2][:, :w.joints], share.dev_sets[i % share.n_sets][2])
+            e1.record(stream)
+            barrier()
+            sa_ms = e0.elapsed_time(e1) / steps
+            entry["soft_argmax"] = {"joints": w.joints, "ms": sa_ms, "algorithmic_bytes": w.soft_argmax_bytes(),
+                                    "roofline_frac": w.soft_argmax_bytes() / (sa_ms * 1e-3) / 1e9 / peak}
+        block[name] = entry
+        del share
+        torch.cuda.empty_cache()
+    return block
+
+
+def backward_block(dev, stream, barrier, peak):
+    """Gradient w.r.t. the feature maps (training goes through it, train.py:110): sum / max / softmax at
+    cfg2 and cfg4.  Algorithmic bytes: grad_out read once, features read once (max / softmax re-sample),
+    gradient written once."""
+    from multiviewhmr_b200 import autograd
+    block = {}
+    for name in ("cfg2", "cfg4"):
+        w = syn.CONFIGS[name]
+        f, P, cv, _ = syn.make_inputs(w)
+        fd, Pd, cvd = (t.to(dev) for t in (f, P, cv))
+        g = torch.randn((w.B, w.C, w.G, w.G, w.G), device=dev)
+        alg = w.B * w.C * w.G ** 3 * 4 + 2 * w.B * w.V * w.C * w.H * w.W * 4 + w.B * w.G ** 3 * 12
+        steps = 20 if name == "cfg2" else 6
+        for method in ("sum", "max", "softmax"):
+            for _ in range(2):
+                autograd.unprojection_backward(g, fd, Pd, cvd, method)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(steps):
+                autograd.unprojection_backward(g, fd, Pd, cvd, method)
+            e1.record(stream)
+            barrier()
+            ms = e0.elapsed_time(e1) / steps
+            block["%s_%s" % (name, method)] = {"ms": ms, "algorithmic_bytes": alg,
+                                               "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "steps": steps}
+        del fd, cvd, g
+        torch.cuda.empty_cache()
+    return block
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="cfg2", choices=sorted(syn.CONFIGS))
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(syn.CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-config and backward blocks (N=1)")
     args = ap.parse_args()
     w = syn.CONFIGS[args.workload]
     if args.impl == "reference":
@@ -192,169 +436,76 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize(dev)
 
-    # rotating input sets: more input bytes in flight than the 126 MB L2 holds
-    in_bytes = w.B * w.V * w.C * w.H * w.W * (2 if w.dtype == "bf16" else 4) + w.B * w.G ** 3 * 12
-    n_sets = max(2, -(-2 * L2_BYTES // in_bytes))
-    host_sets, dev_sets = [], []
-    for i in range(n_sets):
-        f, P, cv, _ = syn.make_inputs(w, seed=1234 + 97 * rank + i)
-        if w.dtype == "bf16":
-            f = f.bfloat16()
-        host = tuple(t.pin_memory() for t in (f, P, cv))
-        host_sets.append(host)
-        dev_sets.append(tuple(t.to(dev) for t in host))
-    outs = [torch.empty((w.B, w.C, w.G, w.G, w.G), dtype=torch.float32, device=dev) for _ in range(2)]
     stream = torch.cuda.current_stream(dev)
-
-    # ---- device-resident timing: K steps of (pack + fused kernel) ------------------
-    kern_ev = []
-
-    def step(i, timed):
-        f, P, cv = dev_sets[i % n_sets]
-        packed = agg.pack_features(f)                                   # launch 1
-        if timed:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
-        agg.unprojection(f, P, cv, w.method, out=outs[i % 2], packed=packed)   # launch 2
-        if timed:
-            e1.record(stream)
-            kern_ev.append((e0, e1))
-
-    for i in range(args.warmup):
-        step(i, False)
+    peak, peak_src = measured_peak()
+    share = RankShare(w, rank, world, dev)
     sampler = ClockSampler(dev)
-    barrier()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with sampler:
-        t_start.record(stream)
-        for i in range(args.steps):
-            step(i, True)
-        t_end.record(stream)
-        barrier()
-    elapsed_ms = t_start.elapsed_time(t_end)
-    kernel_ms = sum(a.elapsed_time(b) for a, b in kern_ev) / len(kern_ev)
-    launches = 2 * args.steps
 
-    # ---- informative extra: the same step when the producer hands over channels-last maps, which the
-    # kernel gathers in place (MVHMR_LAYOUT_NHWC: no pack_kernel).  Not the headline: the reference's
-    # backbone emits NCHW, which is what `value` is measured on.
-    cl_sets = [f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3) for f, _, _ in dev_sets]
-    cl_ok = agg._is_channels_last(cl_sets[0])
-    cl_ms = None
-    if cl_ok:
-        for i in range(args.warmup):
-            agg.unprojection(cl_sets[i % n_sets], dev_sets[i % n_sets][1], dev_sets[i % n_sets][2], w.method, out=outs[i % 2])
-        barrier()
-        c_start, c_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        c_start.record(stream)
-        for i in range(args.steps):
-            agg.unprojection(cl_sets[i % n_sets], dev_sets[i % n_sets][1], dev_sets[i % n_sets][2], w.method, out=outs[i % 2])
-        c_end.record(stream)
-        barrier()
-        cl_ms = c_start.elapsed_time(c_end) / args.steps
-    del cl_sets
+    # ---- device-resident timing: K steps of (pack + fused kernel) over this rank's windows ----
+    ms_per_step, kernel_ms = time_device_resident(agg, share, args.steps, args.warmup, stream, barrier, sampler)
 
-    # ---- end to end: pinned host inputs -> public API -> metric back on the host ------
-    e2e_steps = max(5, min(args.steps, 30))
-    metric_host = torch.empty((w.B, w.C, 3), dtype=torch.float32).pin_memory()
-    d2h = metric_host.numel() * 4
-    # Host inputs of a step, as in VolumeGenerator.forward (models/aggregation.py:119-193): feature maps,
-    # projection matrices and the per-sample cuboid centre / rotation; the coordinate volume itself is
-    # built on the device (the reference builds it there too, :150-187).
-    rots_np = np.stack([np.eye(3, dtype=np.float32)] * w.B)
-    centers_sets = [syn.make_inputs(syn.Workload("c", w.B, 1, 1, 1, 1, 2), seed=1234 + 97 * rank + i)[3].numpy()
-                    for i in range(n_sets)]
-    h2d = sum(t.numel() * t.element_size() for t in host_sets[0][:2]) + w.B * 12 * 4
-
-    # Double-buffered: the host->device copies of step i+1 run on a copy stream while step i
-    # computes; every copy and every kernel of all e2e steps is inside the timed region.
-    copy_stream = torch.cuda.Stream(device=dev)
-    dev_in = [tuple(torch.empty_like(t, device=dev) for t in host_sets[0][:2]) for _ in range(2)]
-    grid_in = [None, None]
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-
-    def stage(i):
-        slot = i % 2
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])            # the slot's previous user is done
-            for d, h in zip(dev_in[slot], host_sets[i % n_sets][:2]):
-                d.copy_(h, non_blocking=True)
-            grid_in[slot] = agg.build_coord_volumes(centers_sets[i % n_sets], rots_np, w.G, w.cuboid_side, dev)
-            copied[slot].record(copy_stream)
-
-    def e2e_run(n):
-        for ev in consumed:
-            ev.record(stream)
-        stage(0)
-        for i in range(n):
-            slot = i % 2
-            if i + 1 < n:
-                stage(i + 1)
-            stream.wait_event(copied[slot])
-            f, P = dev_in[slot]
-            cv = grid_in[slot]
-            cv.record_stream(stream)
-            vol = agg.unprojection(f, P, cv, w.method, out=outs[slot])   # pack + fused kernel
-            joints = agg.soft_argmax_3d(vol, cv)                         # the step's metric: (B,C,3) expectations
-            metric_host.copy_(joints, non_blocking=True)
-            consumed[slot].record(stream)
-
-    e2e_run(3)
-    barrier()
-    # three repetitions of e2e_steps steps, median reported: one host hiccup (page faults of a fresh box,
-    # a pinned-pool growth) otherwise decides the whole number
-    e2e_reps = []
-    with sampler:
-        for _ in range(3):
-            e_start, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e_start.record(stream)
-            e2e_run(e2e_steps)
-            e_end.record(stream)
-            barrier()
-            e2e_reps.append(e_start.elapsed_time(e_end))
-    e2e_ms = sorted(e2e_reps)[1]
+    # ---- end to end: pinned host inputs -> public API -> result back in pinned host memory ----
+    e2e_steps = max(4, min(args.steps, 8 if share.out_bytes > (1 << 30) else 20))
+    e2e_ms, e2e_reps, h2d, d2h = time_e2e(agg, share, e2e_steps, stream, barrier, dev, True, sampler)
+    gpu_ms, gpu_reps, _, gpu_d2h = time_e2e(agg, share, e2e_steps, stream, barrier, dev, False, sampler)
 
     if world > 1:
-        t = torch.tensor([elapsed_ms, e2e_ms, kernel_ms, cl_ms or 0.0], device=dev)
+        t = torch.tensor([ms_per_step, e2e_ms, kernel_ms, gpu_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, e2e_ms, kernel_ms, cl_max = (float(x) for x in t.cpu())
-        cl_ms = cl_max if cl_ok else None
+        ms_per_step, e2e_ms, kernel_ms, gpu_ms = (float(x) for x in t.cpu())
+        cnt = torch.tensor([float(share.units), float(share.launches_per_step())], device=dev, dtype=torch.float64)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_units, launches_per_step = float(cnt[0]), int(cnt[1])
+    else:
+        total_units, launches_per_step = float(share.units), share.launches_per_step()
+    assert total_units == float(w.vcv), (total_units, w.vcv)
 
     if rank == 0:
-        units = w.vcv * world
-        ms_per_step = elapsed_ms / args.steps
-        value = units / (ms_per_step * 1e-3) / 1e9
-        peak, peak_src = measured_peak()
+        value = total_units / (ms_per_step * 1e-3) / 1e9
+        # roofline of the fused kernel: the slowest rank's launches cover 1/world of the algorithmic bytes
         alg = w.algorithmic_bytes()
-        achieved = alg / (kernel_ms * 1e-3) / 1e9
+        alg_rank = alg / world
+        achieved = alg_rank / (kernel_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "bf16" if w.dtype == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": describe(w), "per_gpu_batch": w.B, "parallelism": "batch-sharded x%d, no collective" % world,
-                       "l2": "%d rotating input sets (%.0f MB > 126 MB L2), outputs double-buffered" % (n_sets, n_sets * in_bytes / 1e6),
-                       "step": "pack_kernel + unproject_kernel", "tile": os.environ.get("MVHMR_TILE", "auto")},
+            "config": config_of(w, world),
+            "notes": {"per_gpu_batch": w.B / world,
+                      "l2": "%d rotating input set(s) of %.0f MB per rank + %.0f MB of output per step (L2 = 126 MB), outputs double-buffered"
+                            % (share.n_sets, share.in_bytes / 1e6, share.out_bytes / 1e6),
+                      "step": "pack_kernel + fused unproject/aggregate kernel", "path": os.environ.get("MVHMR_PATH", "auto")},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(w.name), "kernel": "unproject_kernel",
-                         "kernel_ms": kernel_ms, "algorithmic_bytes": alg, "peak_source": peak_src,
-                         "step_frac": (alg / (ms_per_step * 1e-3) / 1e9) / peak},
-            "e2e": {"value": units / (e2e_ms / e2e_steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                    "repetitions_ms_per_step": [t / e2e_steps for t in e2e_reps],
-                    "path": "pinned host features+proj+centres -> (copy stream, double-buffered) build_coord_volumes() -> unprojection() -> soft_argmax_3d() -> host"},
-            "gpu_launches": launches * world,
+                         "traffic": recorded_traffic(w.name), "kernel": "fused unproject+aggregate kernel",
+                         "kernel_ms": kernel_ms, "algorithmic_bytes": alg_rank, "peak_source": peak_src,
+                         "step_frac": (alg_rank / (ms_per_step * 1e-3) / 1e9) / peak,
+                         "nominal_8tbs_frac": achieved / 8000.0},
+            "e2e": {"value": total_units / (e2e_ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_ms,
+                    "repetitions_ms_per_step": e2e_reps,
+                    "h2d_gbs_per_rank": h2d / (e2e_ms * 1e-3) / 1e9, "d2h_gbs_per_rank": d2h / (e2e_ms * 1e-3) / 1e9,
+                    "path": "pinned host features+proj+centres -> copy-in stream (+ build_coord_volumes()) -> pack_features() + unprojection() -> "
+                            "copy-out stream -> the full (B,C,G,G,G) volume in pinned host memory (bytes are per rank)",
+                    "consumer_on_gpu": {"value": total_units / (gpu_ms * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": gpu_ms,
+                                        "d2h_bytes_per_step": gpu_d2h,
+                                        "path": "same inputs; the volume stays on the GPU, soft_argmax_3d() -> (B,C,3) to host"}},
+            "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(),
         }
-        if cl_ms:
-            line["extras"] = {"channels_last_in_place": {
-                "ms_per_step": cl_ms, "value": units / (cl_ms * 1e-3) / 1e9, "unit": UNIT,
-                "note": "same workload, feature maps handed over as (B,V,H,W,C): unproject_kernel only, no pack_kernel"}}
+        if world == 1 and not args.no_extras:
+            head = {"workload": describe(w), "ms_per_step": ms_per_step, "kernel_ms": kernel_ms, "value": value, "unit": UNIT,
+                    "algorithmic_bytes": alg, "roofline_frac": achieved / peak,
+                    "step_frac": line["roofline"]["step_frac"], "steps": args.steps}
+            del share
+            torch.cuda.empty_cache()
+            line["configs"] = per_config_block(agg, dev, stream, barrier, peak, w.name, head)
+            line["extras"] = {"backward": backward_block(dev, stream, barrier, peak)}
         if world == 1 and not args.no_cpu_baseline:
-            val, sec, cores, sample = cpu_reference_sample(w, steps=2, warmup=1)
+            val, sec, cores, sample = cpu_reference_sample(w, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier(device_ids=[local_rank])
         dist.destroy_process_group()
 
 

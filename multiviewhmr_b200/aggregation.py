@@ -90,8 +90,17 @@ def unprojection(features, proj_matricies, coord_volumes, aggregation_method='so
         raise ValueError("shape mismatch: features %s, proj_matricies %s, coord_volumes %s"
                          % (tuple(features.shape), tuple(proj_matricies.shape), tuple(coord_volumes.shape)))
     if torch.is_grad_enabled() and features.requires_grad:
+        if out is not None:
+            raise ValueError("unprojection: `out=` cannot be combined with autograd (features.requires_grad); "
+                             "use the returned tensor or call under torch.no_grad()")
+        if window is not None:
+            b0, b1, n0, n1 = (int(v) for v in window)
+            N = int(np.prod(coord_volumes.shape[1:4]))
+            if not (0 <= b0 <= b1 <= B and 0 <= n0 <= n1 <= N):
+                raise ValueError("unprojection: shard window %r outside B=%d N=%d" % (tuple(window), B, N))
         from .autograd import unprojection_with_grad
-        return unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method)
+        return unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method,
+                                      window=window, packed=packed)
     gx, gy, gz = (int(v) for v in coord_volumes.shape[1:4])
     coord = coord_volumes.detach().float().contiguous()
     return _launch_unprojection(features, proj_matricies, (gx, gy, gz), aggregation_method, window, out, packed,
@@ -153,9 +162,11 @@ def unprojection_grid(features, proj_matricies, centers, rotations, volume_size,
     if features.dim() != 5 or tuple(proj_matricies.shape) != (B, V, 3, 4):
         raise ValueError("expected features (B,V,C,H,W) and proj_matricies (B,V,3,4), got %s and %s"
                          % (tuple(features.shape), tuple(proj_matricies.shape)))
+    _check_grid_arrays(centers, rotations, B)
     if torch.is_grad_enabled() and features.requires_grad:
         coord_volumes = build_coord_volumes(centers, rotations, volume_size, cuboid_side, dev)
-        return unprojection(features, proj_matricies, coord_volumes, aggregation_method)
+        return unprojection(features, proj_matricies, coord_volumes, aggregation_method,
+                            window=window, out=out, packed=packed)
     G = int(volume_size)
     dev_buf = _grid_buffer(centers, rotations, dev)
     grid = _lib.Grid()
@@ -168,6 +179,14 @@ def unprojection_grid(features, proj_matricies, centers, rotations, volume_size,
         grid.step[k] = float(step)
     return _launch_unprojection(features, proj_matricies, (G, G, G), aggregation_method, window, out, packed,
                                 grid=grid)
+
+
+def _check_grid_arrays(centers, rotations, B):
+    """centers (B,3), rotations (B,3,3): the kernels index them by sample, so a short or
+    mis-shaped host array would be an out-of-bounds device read."""
+    cs, rs = np.shape(centers), np.shape(rotations)
+    if tuple(cs) != (B, 3) or tuple(rs) != (B, 3, 3):
+        raise ValueError("expected centers (%d,3) and rotations (%d,3,3), got %s and %s" % (B, B, cs, rs))
 
 
 def _grid_buffer(centers, rotations, device):
@@ -277,6 +296,7 @@ def soft_argmax_3d_grid(volumes, centers, rotations, cuboid_side):
     if volumes.dim() != 5 or volumes.dtype != torch.float32:
         raise ValueError("expected float32 volumes (B,J,Gx,Gy,Gz), got %s %s" % (volumes.dtype, tuple(volumes.shape)))
     B, J, gx, gy, gz = (int(v) for v in volumes.shape)
+    _check_grid_arrays(centers, rotations, B)
     L = _lib.load()
     vol, sample_stride = _leading_channels_view(volumes)
     dev_buf = _grid_buffer(centers, rotations, dev)
@@ -341,7 +361,8 @@ def build_coord_volumes(centers, rotations, volume_size, cuboid_side, device):
     meshgrid / affine / mm sequence."""
     centers = np.ascontiguousarray(centers, dtype=np.float32)
     rotations = np.ascontiguousarray(rotations, dtype=np.float32)
-    B = centers.shape[0]
+    B = centers.shape[0] if centers.ndim else 0
+    _check_grid_arrays(centers, rotations, B)
     G = int(volume_size)
     # position = base_point - sides/2 with base_point (0,0,0); python floats are
     # cast to fp32 by torch when they meet the fp32 grid (`:156-158`)
@@ -429,23 +450,31 @@ class VolumeGenerator(nn.Module):
         batched GEMM whose output is pixel-major, (B,V,H,W,C) — the layout the fused kernel gathers
         in place (`MVHMR_LAYOUT_NHWC`), so neither a transposition nor the pack pass is paid
         (B8 V4 256->32 ch 96x96 on B200: 132 us against 212 + 20 us for cuDNN conv + pack in fp32, 73 against
-        87 + 20 us with TF32).  The GEMM obeys `torch.backends.cuda.matmul.allow_tf32`, the conv
-        `torch.backends.cudnn.allow_tf32`; the GEMM route is taken only when both flags agree, so the
-        precision the user asked for never changes."""
+        87 + 20 us with TF32).  The conv obeys `torch.backends.cudnn.allow_tf32`; the GEMM is pinned to
+        that same switch for the duration of the call, so the precision the user asked for never
+        changes and the route is taken under PyTorch's default flags too.  `self.last_route` records
+        which route ran ("gemm_channels_last" | "conv")."""
         conv = self.process_feature[0]
         Cin, H, W = features.shape[-3:]
         Cout = conv.out_channels
         pixel = Cout * features.element_size()
         needs_grad = torch.is_grad_enabled() and (features.requires_grad or conv.weight.requires_grad)
-        same_precision = bool(torch.backends.cuda.matmul.allow_tf32) == bool(torch.backends.cudnn.allow_tf32)
-        if (self.channels_last and not needs_grad and same_precision and conv.bias is not None
+        if (self.channels_last and not needs_grad and conv.bias is not None
                 and features.dtype == conv.weight.dtype
                 and pixel >= 16 and pixel & (pixel - 1) == 0 and H >= 2 and W >= 2):
             BV = batch_size * n_views
             x = features.reshape(BV, Cin, H * W).transpose(1, 2)                    # (BV, HW, Cin), a view
-            y = torch.matmul(x, conv.weight.detach().view(Cout, Cin).t())           # (BV, HW, Cout) contiguous
+            # the conv this GEMM stands in for obeys cuDNN's TF32 switch: pin the GEMM to it for this call
+            saved = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+            try:
+                y = torch.matmul(x, conv.weight.detach().view(Cout, Cin).t())       # (BV, HW, Cout) contiguous
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = saved
             y += conv.bias.detach()
+            self.last_route = "gemm_channels_last"
             return y.view(batch_size, n_views, H, W, Cout).permute(0, 1, 4, 2, 3)
+        self.last_route = "conv"
         features = features.view(-1, *features.shape[2:])
         features = self.process_feature(features)
         return features.view(batch_size, n_views, *features.shape[1:])

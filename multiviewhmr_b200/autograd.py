@@ -13,20 +13,34 @@ from . import _lib
 
 class _Unprojection(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, features, proj_matricies, coord_volumes, aggregation_method):
+    def forward(ctx, features, proj_matricies, coord_volumes, aggregation_method, window, packed):
         from .aggregation import unprojection
         with torch.no_grad():
-            out = unprojection(features.detach(), proj_matricies, coord_volumes, aggregation_method)
+            if window is None:
+                out = unprojection(features.detach(), proj_matricies, coord_volumes, aggregation_method, packed=packed)
+            else:
+                # shard window: voxels outside it are zeros here (and receive no gradient)
+                B, _, C = features.shape[:3]
+                out = torch.zeros((B, C) + tuple(coord_volumes.shape[1:4]), dtype=torch.float32, device=features.device)
+                unprojection(features.detach(), proj_matricies, coord_volumes, aggregation_method,
+                             window=window, out=out, packed=packed)
         ctx.save_for_backward(features, proj_matricies, coord_volumes)
         ctx.method = aggregation_method
+        ctx.window = window
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         features, proj_matricies, coord_volumes = ctx.saved_tensors
-        g, feats, proj, coord = grad_out, features, proj_matricies, coord_volumes
-        gf = unprojection_backward(g, feats, proj, coord, ctx.method)
-        return gf.to(features.dtype), None, None, None
+        g = grad_out
+        if ctx.window is not None:
+            b0, b1, n0, n1 = ctx.window
+            B, C = g.shape[:2]
+            masked = torch.zeros_like(g, memory_format=torch.contiguous_format)
+            masked.view(B, C, -1)[b0:b1, :, n0:n1] = g.reshape(B, C, -1)[b0:b1, :, n0:n1]
+            g = masked
+        gf = unprojection_backward(g, features, proj_matricies, coord_volumes, ctx.method)
+        return gf.to(features.dtype), None, None, None, None, None
 
 
 def unprojection_backward(grad_out, features, proj_matricies, coord_volumes, aggregation_method, simple=False):
@@ -59,5 +73,10 @@ def unprojection_backward(grad_out, features, proj_matricies, coord_volumes, agg
     return gf
 
 
-def unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method):
-    return _Unprojection.apply(features, proj_matricies, coord_volumes, aggregation_method)
+def unprojection_with_grad(features, proj_matricies, coord_volumes, aggregation_method, window=None, packed=None):
+    """Differentiable `unprojection`.  `window=(b0,b1,n0,n1)` restricts both passes to a shard
+    (zeros outside); the result is always a fresh tensor (`out=` cannot be combined with
+    autograd — `aggregation.unprojection` rejects it)."""
+    if window is not None:
+        window = tuple(int(v) for v in window)
+    return _Unprojection.apply(features, proj_matricies, coord_volumes, aggregation_method, window, packed)

@@ -71,30 +71,62 @@ def homogeneous_to_euclidean(points):
     raise TypeError("Works only with numpy arrays and PyTorch tensors.")
 
 
+class _ProjectPoints(torch.autograd.Function):
+    """Kernel forward (`mvhmr_project_points`), analytic backward.  The reference's torch branch
+    is differentiable (`utils/loss.py:377-378` projects predictions that require grad), so the
+    drop-in has to be as well."""
+
+    @staticmethod
+    def forward(ctx, proj_matrix, points_3d, euclid):
+        dev = points_3d.device
+        P, pts = proj_matrix.detach().contiguous(), points_3d.detach().contiguous()
+        n = pts.shape[0]
+        out = torch.empty((n, 2 if euclid else 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().mvhmr_project_points(
+                _lib.ptr(out), _lib.ptr(P), _lib.ptr(pts), n, int(bool(euclid)), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(P, pts, out)
+        ctx.euclid = bool(euclid)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        P, pts, out = ctx.saved_tensors
+        grad = grad.contiguous()
+        if ctx.euclid:
+            # out = h[:, :2] / w with h = [p 1] P^T, w = h[:, 2]
+            w = (pts @ P[2, :3] + P[2, 3]).unsqueeze(1)
+            g_xy = grad / w
+            g_w = -(g_xy * out).sum(dim=1, keepdim=True)
+            g_h = torch.cat([g_xy, g_w], dim=1)
+        else:
+            g_h = grad
+        g_pts = g_h @ P[:, :3] if ctx.needs_input_grad[1] else None
+        g_P = None
+        if ctx.needs_input_grad[0]:
+            ones = torch.ones((pts.shape[0], 1), dtype=pts.dtype, device=pts.device)
+            g_P = g_h.t() @ torch.cat([pts, ones], dim=1)
+        return g_P, g_pts, None
+
+
 def project_3d_points_to_image_plane_without_distortion(proj_matrix, points_3d, convert_back_to_euclidean=True):
     """Project (N,3) points with a 3x4 matrix; reference `:89-110`.
 
     numpy in -> numpy out (host, float64 as given).  torch in -> CUDA kernel
-    with the reference's fp32 rounding (K=4 FMA chain), (N,2) or (N,3) out."""
+    with the reference's fp32 rounding (K=4 FMA chain), (N,2) or (N,3) out;
+    differentiable w.r.t. both arguments like the reference's torch ops."""
     if isinstance(proj_matrix, np.ndarray) and isinstance(points_3d, np.ndarray):
         result = euclidean_to_homogeneous(points_3d) @ proj_matrix.T
         return homogeneous_to_euclidean(result) if convert_back_to_euclidean else result
     if torch.is_tensor(proj_matrix) and torch.is_tensor(points_3d):
-        dev = _lib.require_cuda(points_3d, proj_matrix)
+        _lib.require_cuda(points_3d, proj_matrix)
         if points_3d.dtype != torch.float32 or proj_matrix.dtype != torch.float32:
             raise TypeError("multiviewhmr_b200: projection kernel is fp32 (got %s, %s)"
                             % (proj_matrix.dtype, points_3d.dtype))
         if proj_matrix.shape != (3, 4) or points_3d.dim() != 2 or points_3d.shape[1] != 3:
             raise ValueError("expected proj_matrix (3,4) and points_3d (N,3), got %s and %s"
                              % (tuple(proj_matrix.shape), tuple(points_3d.shape)))
-        P, pts = proj_matrix.contiguous(), points_3d.contiguous()
-        n = pts.shape[0]
-        out = torch.empty((n, 2 if convert_back_to_euclidean else 3), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(_lib.load().mvhmr_project_points(
-                _lib.ptr(out), _lib.ptr(P), _lib.ptr(pts), n, int(bool(convert_back_to_euclidean)),
-                _lib.stream_ptr(dev)))
-        return out
+        return _ProjectPoints.apply(proj_matrix, points_3d, bool(convert_back_to_euclidean))
     raise TypeError("Works only with numpy arrays and PyTorch tensors.")
 
 

@@ -65,11 +65,25 @@ def unprojection_sharded(features, proj_matricies, coord_volumes, aggregation_me
 
     Returns (out, windows): `out` is a full-size (B,C,Gx,Gy,Gz) buffer in which
     only the rank's windows are written (bit-identical to the unsharded call
-    there)."""
+    there).  When the feature maps require grad the windows go through autograd
+    (`out=` is then not allowed): the returned tensor is zero outside the rank's
+    windows and its backward only sees the gradient inside them."""
     from .aggregation import unprojection
     B = features.shape[0]
     gx, gy, gz = (int(v) for v in coord_volumes.shape[1:4])
     wins = shard_windows(B, gx, rank, world_size)
+    if torch.is_grad_enabled() and features.requires_grad:
+        if out is not None:
+            raise ValueError("unprojection_sharded: `out=` cannot be combined with autograd")
+        total = None
+        for w in wins:
+            n0, n1 = w.voxels(gy, gz)
+            part = unprojection(features, proj_matricies, coord_volumes, aggregation_method,
+                                window=(w.b0, w.b1, n0, n1))
+            total = part if total is None else total + part
+        if total is None:
+            total = torch.zeros((B, features.shape[2], gx, gy, gz), dtype=torch.float32, device=features.device)
+        return total, wins
     if out is None:
         out = torch.zeros((B, features.shape[2], gx, gy, gz), dtype=torch.float32, device=features.device)
     for w in wins:

@@ -80,11 +80,12 @@ def ring_projection(b, v, V, H, W, cuboid_side=2500.0, distance=4500.0, behind=F
     return K @ np.hstack([R, t])
 
 
-def make_projections(B, V, H, W, cuboid_side=2500.0, behind_views=()):
+def make_projections(B, V, H, W, cuboid_side=2500.0, behind_views=(), b_offset=0):
+    """(B,V,3,4) fp32 projections of samples [b_offset, b_offset + B) of the ring-camera set."""
     P = np.zeros((B, V, 3, 4), dtype=np.float64)
     for b in range(B):
         for v in range(V):
-            P[b, v] = ring_projection(b, v, V, H, W, cuboid_side, behind=(v in behind_views))
+            P[b, v] = ring_projection(b + b_offset, v, V, H, W, cuboid_side, behind=(v in behind_views))
     return torch.from_numpy(P).float()
 
 
@@ -129,12 +130,14 @@ def rotation_matrix(axis, theta):
         [2 * (b * d + a * c), 2 * (c * d - a * b), a * a + d * d - b * b - c * c]])
 
 
-def make_inputs(w, seed=1234, theta=0.0, behind_views=(), H=None, W=None):
+def make_inputs(w, seed=1234, theta=0.0, behind_views=(), H=None, W=None, b_offset=0):
     """(features, proj, coord_volumes, centers) on the host for workload `w`.
 
     features (B,V,C,H,W) fp32 N(0,1) — for bf16 workloads already rounded to
     bf16 values (still returned as fp32; cast with `.bfloat16()` is lossless),
     proj (B,V,3,4) fp32, coord_volumes (B,G,G,G,3) fp32, centers (B,3) fp32.
+    `b_offset` shifts the sample index the ring cameras are built from (a rank that
+    owns samples [b_offset, b_offset + B) of a larger batch).
     """
     H = w.H if H is None else H
     W = w.W if W is None else W
@@ -143,6 +146,6 @@ def make_inputs(w, seed=1234, theta=0.0, behind_views=(), H=None, W=None):
     centers = torch.randn(w.B, 3, generator=g) * 100.0
     if w.dtype == "bf16":
         feats = feats.bfloat16().float()
-    proj = make_projections(w.B, w.V, H, W, w.cuboid_side, behind_views)
+    proj = make_projections(w.B, w.V, H, W, w.cuboid_side, behind_views, b_offset)
     coord = make_coord_volumes(centers, w.G, w.cuboid_side, theta)
     return feats, proj, coord, centers

@@ -1,0 +1,231 @@
+"""Round-2 GPU parity cases: BASELINE configs #4 and #5 at full grid size, the
+shard windows of the cfg5 scaling sweep, both fused-kernel designs against each
+other, and the drop-in behaviours the advisor flagged (autograd through the
+projection helper, sharded training, default-flag GEMM route, shape checks)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from multiviewhmr_b200 import _lib, aggregation as agg, multiview, sharding, synthetic as syn
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+OUR_TOL_SOFTMAX = 1e-6
+SPEC_TOL_FP32 = 1e-5
+
+
+def cuda(*arrays):
+    return [torch.as_tensor(a).to(DEV) for a in arrays]
+
+
+def sub_workload(w, B):
+    return syn.Workload(w.name, B, w.V, w.C, w.H, w.W, w.G, w.method, w.dtype, w.joints, w.cuboid_side)
+
+
+# ---------------------------------------------------------------- cfg4 / cfg5 at full grid size
+@pytest.mark.parametrize("method", ["softmax", "max"])
+def test_cfg4_full_grid_against_oracle(method):
+    """BASELINE config #4 (V8 C64 128x128 -> 64^3): two samples of the full grid against the C
+    restatement (softmax within ex2.approx noise, max bit-exact), then the whole B=16 batch
+    through size-independent properties (sample b of the batch call == the same sample alone)."""
+    w = syn.CONFIGS["cfg4"]
+    f, P, cv, _ = syn.make_inputs(sub_workload(w, 2))
+    got = agg.unprojection(*cuda(f, P, cv), method).cpu().numpy()
+    ref = oracle.unprojection(f, P, cv, method)
+    if method == "softmax":
+        assert rel_l2(got, ref) < OUR_TOL_SOFTMAX
+    else:
+        assert np.array_equal(got, ref)
+
+
+def test_cfg4_full_batch_is_sample_wise_consistent():
+    w = syn.CONFIGS["cfg4"]
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    full = agg.unprojection(fd, Pd, cvd, "softmax")
+    assert full.shape == (16, 64, 64, 64, 64)
+    for b in (0, 7, 15):
+        one = agg.unprojection(fd[b:b + 1].contiguous(), Pd[b:b + 1].contiguous(), cvd[b:b + 1].contiguous(), "softmax")
+        assert torch.equal(one[0], full[b])
+    ref = oracle.unprojection(f[15:16], P[15:16], cv[15:16], "softmax")
+    assert rel_l2(full[15:16].cpu().numpy(), ref) < OUR_TOL_SOFTMAX
+    del full
+
+
+@pytest.mark.parametrize("method", ["softmax", "sum"])
+def test_cfg5_full_grid_against_oracle(method):
+    """BASELINE config #5 (V8 C32 96x96 -> 80^3, gz = 80 is not a multiple of 32): two samples of
+    the full grid against the C restatement."""
+    w = syn.CONFIGS["cfg5"]
+    f, P, cv, _ = syn.make_inputs(sub_workload(w, 2))
+    got = agg.unprojection(*cuda(f, P, cv), method).cpu().numpy()
+    ref = oracle.unprojection(f, P, cv, method)
+    if method == "softmax":
+        assert rel_l2(got, ref) < OUR_TOL_SOFTMAX
+    else:
+        assert np.array_equal(got, ref)
+
+
+def test_cfg5_shard_windows_are_bitwise_identical_to_the_unsharded_call():
+    """All shard_windows of the B=64 cfg5 problem at 2/4/8 ranks (batch split) and at a world size
+    that forces x-slabs, computed on one GPU, compared bit for bit with the unsharded call."""
+    w = syn.CONFIGS["cfg5"]
+    B = 8                                      # the windows are per (sample, x-plane): 8 samples exercise them all
+    f, P, cv, _ = syn.make_inputs(sub_workload(w, B))
+    fd, Pd, cvd = cuda(f, P, cv)
+    full = agg.unprojection(fd, Pd, cvd, "softmax")
+    for world in (2, 4, 8, 3, 16):
+        out = torch.full_like(full, float("nan"))
+        seen = 0
+        for r in range(world):
+            _, wins = sharding.unprojection_sharded(fd, Pd, cvd, "softmax", r, world, out=out)
+            seen += sum(x.units() for x in wins)
+        assert seen == B * w.G
+        assert torch.equal(out, full), world
+    # the windows the B=64 sweep really uses
+    for world in (1, 2, 4, 8):
+        wins = [sharding.shard_windows(64, w.G, r, world) for r in range(world)]
+        assert all(len(x) == 1 and x[0].x0 == 0 and x[0].x1 == w.G and x[0].b1 - x[0].b0 == 64 // world for x in wins)
+    del full, out
+
+
+# ---------------------------------------------------------------- both kernel designs agree
+@pytest.mark.parametrize("case", [("cfg1", "sum"), ("cfg1", "softmax"), ("cfg2s", "softmax"), ("cfg5s", "softmax"),
+                                  ("cfg4s", "mean"), ("cfg3s", "softmax"), ("rot", "max")])
+def test_staged_and_gather_kernels_agree_bitwise(case, monkeypatch):
+    """The shared-memory-staged kernel and the L1-gather kernel do the same IEEE operations in the
+    same order: their results must be equal bit for bit, in every fusion mode."""
+    name, method = case
+    table = {"cfg1": syn.CONFIGS["cfg1"], "cfg2s": sub_workload(syn.CONFIGS["cfg2"], 1),
+             "cfg3s": sub_workload(syn.CONFIGS["cfg3"], 1), "cfg4s": sub_workload(syn.CONFIGS["cfg4"], 1),
+             "cfg5s": sub_workload(syn.CONFIGS["cfg5"], 1),
+             "rot": syn.Workload("rot", 2, 4, 32, 48, 40, 24)}
+    w = table[name]
+    f, P, cv, _ = syn.make_inputs(w, theta=0.7 if name == "rot" else 0.0, behind_views=(1,) if name == "rot" else ())
+    fd, Pd, cvd = cuda(f, P, cv)
+    if w.dtype == "bf16":
+        fd = fd.bfloat16()
+    monkeypatch.setenv("MVHMR_PATH", "gather")
+    a = agg.unprojection(fd, Pd, cvd, method)
+    monkeypatch.setenv("MVHMR_PATH", "staged")
+    b = agg.unprojection(fd, Pd, cvd, method)
+    assert torch.equal(a, b)
+    pixel = w.C * fd.element_size()
+    if pixel >= 16 and pixel & (pixel - 1) == 0:
+        fcl = fd.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        assert torch.equal(agg.unprojection(fcl, Pd, cvd, method), a)
+
+
+# ---------------------------------------------------------------- advisor findings
+def test_projection_helper_is_differentiable_like_the_reference():
+    """`utils/loss.py:377-378` projects predicted 3-D keypoints (requires_grad) through this helper; the
+    2-D reprojection loss must reach them."""
+    g = torch.Generator().manual_seed(0)
+    P = torch.tensor(syn.ring_projection(0, 1, 4, 96, 96), dtype=torch.float32)
+    pts = (torch.randn(17, 3, generator=g) * 300.0)
+    target = torch.rand(17, 2, generator=g) * 96.0
+    for euclid in (True, False):
+        # the reference's torch ops (utils/multiview.py:89-110) on the CPU
+        pr, Pr = pts.clone().requires_grad_(True), P.clone().requires_grad_(True)
+        h = torch.cat([pr, torch.ones(17, 1)], dim=1) @ Pr.t()
+        ref = (h.t()[:-1] / h.t()[-1]).t() if euclid else h
+        tgt = target if euclid else torch.cat([target, torch.ones(17, 1)], dim=1)
+        ((ref - tgt) ** 2).mean().backward()
+        pd, Pd = pts.to(DEV).requires_grad_(True), P.to(DEV).requires_grad_(True)
+        out = multiview.project_3d_points_to_image_plane_without_distortion(Pd, pd, euclid)
+        assert out.requires_grad and out.grad_fn is not None
+        ((out - tgt.to(DEV)) ** 2).mean().backward()
+        assert torch.allclose(out.detach().cpu(), ref.detach(), rtol=1e-5, atol=1e-3)
+        assert rel_l2(pd.grad.cpu().numpy(), pr.grad.numpy()) < 1e-4
+        assert rel_l2(Pd.grad.cpu().numpy(), Pr.grad.numpy()) < 1e-4
+    # without grad the helper stays a plain kernel call
+    out = multiview.project_3d_points_to_image_plane_without_distortion(P.to(DEV), pts.to(DEV))
+    assert not out.requires_grad
+
+
+def test_sharded_unprojection_with_autograd():
+    """Training over shard windows: forward equals the unsharded forward inside the windows (zeros
+    outside), `out=` is rejected instead of silently ignored, and the sum of the ranks' feature
+    gradients is the unsharded gradient."""
+    w = syn.Workload("t", B=3, V=4, C=8, H=24, W=24, G=10)
+    f, P, cv, _ = syn.make_inputs(w, seed=21)
+    fd, Pd, cvd = cuda(f, P, cv)
+    gout = torch.randn(3, 8, 10, 10, 10, device=DEV)
+    full_in = fd.clone().requires_grad_(True)
+    full = agg.unprojection(full_in, Pd, cvd, "softmax")
+    full.backward(gout)
+    world = 2                                   # 3 samples over 2 ranks: one rank gets an x-slab
+    grads, covered = [], torch.zeros_like(full, dtype=torch.bool)
+    for r in range(world):
+        fi = fd.clone().requires_grad_(True)
+        out, wins = sharding.unprojection_sharded(fi, Pd, cvd, "softmax", r, world)
+        assert out.requires_grad
+        mask = torch.zeros_like(covered)
+        for x in wins:
+            mask[x.b0:x.b1, :, x.x0:x.x1] = True
+        assert torch.equal(out.detach()[mask], full.detach()[mask])
+        assert float(out.detach()[~mask].abs().max()) == 0.0
+        covered |= mask
+        out.backward(gout)
+        grads.append(fi.grad)
+        with pytest.raises(ValueError):
+            sharding.unprojection_sharded(fi, Pd, cvd, "softmax", r, world, out=torch.zeros_like(full))
+    assert bool(covered.all())
+    assert rel_l2((grads[0] + grads[1]).cpu().numpy(), full_in.grad.cpu().numpy()) < 1e-5
+    with pytest.raises(ValueError):
+        agg.unprojection(full_in, Pd, cvd, "softmax", out=torch.zeros_like(full))
+    with pytest.raises(ValueError):
+        agg.unprojection(full_in, Pd, cvd, "softmax", window=(0, 4, 0, 10))
+
+
+def test_channels_last_gemm_route_runs_under_default_tf32_flags():
+    B, V, Cin, G = 2, 3, 16, 6
+    rng = np.random.default_rng(0)
+    cams = [[multiview.Camera(np.eye(3), [0.0, 0.0, 4000.0 + 100 * v], [[300.0, 0, 32], [0, 300.0, 32], [0, 0, 1]])
+             for _ in range(B)] for v in range(V)]
+    batch = {"images": np.zeros((B, V, 64, 64, 3), np.float32), "cameras": cams,
+             "keypoints_3d": [rng.normal(size=(17, 3)) * 50 for _ in range(B)]}
+    vg = agg.VolumeGenerator(volume_size=G, input_channels=Cin, output_channels=8, cuboid_side=2000.0, device=DEV)
+    vg.eval()
+    feats = torch.randn(B, V, Cin, 16, 16, device=DEV)
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    try:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = False, True     # PyTorch's defaults
+        with torch.no_grad():
+            a = vg(feats, torch.zeros(B, V, 3, 4, device=DEV), batch)
+        assert vg.last_route == "gemm_channels_last"
+        assert torch.backends.cuda.matmul.allow_tf32 is False                                   # restored
+        vg.channels_last = False
+        with torch.no_grad():
+            b = vg(feats, torch.zeros(B, V, 3, 4, device=DEV), batch)
+        assert vg.last_route == "conv"
+        assert rel_l2(a.cpu().numpy(), b.cpu().numpy()) < 5e-3                                  # both TF32 contractions
+        torch.backends.cudnn.allow_tf32 = False
+        vg.channels_last = True
+        with torch.no_grad():
+            c = vg(feats, torch.zeros(B, V, 3, 4, device=DEV), batch)
+        vg.channels_last = False
+        with torch.no_grad():
+            d = vg(feats, torch.zeros(B, V, 3, 4, device=DEV), batch)
+        assert rel_l2(c.cpu().numpy(), d.cpu().numpy()) < SPEC_TOL_FP32                         # both fp32
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+
+
+def test_grid_descriptor_arrays_are_shape_checked():
+    f, P = cuda(torch.zeros(2, 2, 4, 8, 8), torch.zeros(2, 2, 3, 4))
+    good_c, good_r = np.zeros((2, 3), np.float32), np.stack([np.eye(3, dtype=np.float32)] * 2)
+    agg.unprojection_grid(f, P, good_c, good_r, 4, 2500.0, "sum")
+    with pytest.raises(ValueError):
+        agg.unprojection_grid(f, P, good_c[:1], good_r, 4, 2500.0, "sum")
+    with pytest.raises(ValueError):
+        agg.unprojection_grid(f, P, good_c, good_r[:1], 4, 2500.0, "sum")
+    with pytest.raises(ValueError):
+        agg.build_coord_volumes(good_c, good_r.reshape(2, 9)[:, :6], 4, 2500.0, DEV)
+    vol = torch.zeros(2, 3, 4, 4, 4, device=DEV)
+    with pytest.raises(ValueError):
+        agg.soft_argmax_3d_grid(vol, good_c[:1], good_r, 2500.0)
