@@ -70,7 +70,10 @@ def recorded_traffic(workload):
 
 
 class ClockSampler:
-    """SM clock + throttle reasons sampled every few ms while the timed region runs."""
+    """SM clock + throttle reasons sampled while the timed region runs: once when it starts, every
+    50 ms, once when it ends.  (NVML queries share a driver lock with kernel launches: polling every
+    2 ms, as round 1 did, starved the GPU between the two launches of an 8 ms cfg5 step.)"""
+    PERIOD = 0.05
     REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
                0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
@@ -79,6 +82,8 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = None
         try:
+            if os.environ.get("MVHMR_BENCH_NO_SAMPLER"):
+                raise RuntimeError("sampler disabled")
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
@@ -91,18 +96,21 @@ class ClockSampler:
         except Exception:
             self.nv = None
 
-    def _run(self):
+    def _sample(self):
         nv = self.nv
-        while not self._stop.is_set():
-            try:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-                bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if bits & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.002)
+        try:
+            self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+            bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if bits & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _run(self):
+        while not self._stop.wait(self.PERIOD):
+            self._sample()
+        self._sample()
 
     def __enter__(self):
         if self.nv is not None:

@@ -477,7 +477,7 @@ extern "C" size_t mvhmr_unproject_backward_workspace_bytes(int feat_dtype, int B
 {
     if ((feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16) || B < 0 || V < 1 || C < 1 || H < 1 || W < 1) return 0;
     size_t n = bwd_gpacked_bytes(feat_dtype, B, V, C, H, W);
-    if (method == MVHMR_MAX || method == MVHMR_SOFTMAX) n += mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);
+    if (method == MVHMR_MAX || method == MVHMR_SOFTMAX) n += packed_bytes_layout(feat_dtype, B * V, C, H, W, nchunks_of(feat_dtype, C));
     return n;
 }
 
@@ -538,13 +538,13 @@ extern "C" int mvhmr_unproject_aggregate_backward_ws(const float *grad_out, cons
     cudaError_t e = cudaMemsetAsync(q.gpacked, 0, gbytes, st);
     if (e != cudaSuccess) return fail(MVHMR_ERR_CUDA, "unproject_aggregate_backward: memset: %s", cudaGetErrorString(e));
     if (fwd) {
-        int rc = mvhmr_pack_features(feats, feat_dtype, fpacked, B * V, C, H, W, stream);
+        int rc = pack_features_layout(feats, feat_dtype, fpacked, B * V, C, H, W, nchunks, stream);   // dense pixels
         if (rc != MVHMR_OK) return rc;
     }
     p.packed = fwd ? fpacked : nullptr;
     p.proj = proj; p.coord = coord;
     p.V = V; p.C = C; p.W = W; p.H = H; p.Wp = Wp; p.border = kBorder;
-    p.nchunks = nchunks; p.lpb = ilog2_exact(nchunks) + 4;
+    p.nchunks = nchunks; p.lpb = ilog2_exact(nchunks) + 4; p.pstride = 1 << p.lpb;
     p.plane_bytes = ((long long)Hp * Wp) << p.lpb;
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;

@@ -49,70 +49,6 @@ constexpr int kWarps = MVHMR_WARPS;       // warps per CTA: consecutive x planes
 constexpr unsigned kNotMine = 0xffffffffu;   // view-0 offset of a voxel outside the shard window (real offsets are multiples of 16)
 constexpr int kLzMax = 32;                // voxels of one warp task (z segment): one per lane in phase A
 
-// View fusion of one channel pair; views arrive in order, VMAX at a time.
-//   sum/mean: acc = ((s0 + s1) + s2) ...   (the reference's order)
-//   max     : running max (NaN propagating, like torch.max)
-//   softmax : (m, S = sum e^(s-m), A = sum s*e^(s-m)); result A / S
-template <int METHOD, int VMAX, bool EXACT>
-struct Fuse2 {
-    u64 a, S;
-    float m0, m1;
-    __device__ __forceinline__ void absorb(const u64 *s, int stride, int nv, bool first)
-    {
-        if (METHOD == MVHMR_SUM || METHOD == MVHMR_MEAN) {
-            u64 acc = first ? s[0] : add2(a, s[0]);
-#pragma unroll
-            for (int v = 1; v < VMAX; ++v) if (EXACT || v < nv) acc = add2(acc, s[v * stride]);
-            a = acc;
-        } else if (METHOD == MVHMR_MAX) {
-            f2 x = upk(s[0]);
-            float a0 = first ? x.x : max_nan(m0, x.x), a1 = first ? x.y : max_nan(m1, x.y);
-#pragma unroll
-            for (int v = 1; v < VMAX; ++v) if (EXACT || v < nv) {
-                x = upk(s[v * stride]);
-                a0 = max_nan(a0, x.x); a1 = max_nan(a1, x.y);
-            }
-            m0 = a0; m1 = a1;
-        } else {
-            f2 x = upk(s[0]);
-            float b0 = x.x, b1 = x.y;
-#pragma unroll
-            for (int v = 1; v < VMAX; ++v) if (EXACT || v < nv) {
-                x = upk(s[v * stride]);
-                b0 = fmaxf(b0, x.x); b1 = fmaxf(b1, x.y);
-            }
-            u64 SS = pk(0.0f, 0.0f), AA = SS;
-            if (!first) {
-                const float n0 = fmaxf(m0, b0), n1 = fmaxf(m1, b1);
-                const u64 sc = pk(ex2_approx((m0 - n0) * kLog2e), ex2_approx((m1 - n1) * kLog2e));
-                SS = mul2(S, sc); AA = mul2(a, sc);
-                b0 = n0; b1 = n1;
-            }
-            // exp(s - m) = 2^(s*log2e - m*log2e): one packed FMA for two arguments.  The
-            // rounding of m*log2e is common to all views and cancels in A / S.
-            const u64 L2 = pk(kLog2e, kLog2e), nm = pk(-b0 * kLog2e, -b1 * kLog2e);
-#pragma unroll
-            for (int v = 0; v < VMAX; ++v) if (EXACT || v < nv) {
-                const f2 arg = upk(fma2(s[v * stride], L2, nm));
-                const u64 e = pk(ex2_approx(arg.x), ex2_approx(arg.y));
-                SS = add2(SS, e);
-                AA = fma2(s[v * stride], e, AA);
-            }
-            m0 = b0; m1 = b1; S = SS; a = AA;
-        }
-    }
-    __device__ __forceinline__ f2 result(float Vf) const
-    {
-        if (METHOD == MVHMR_SUM) return upk(a);
-        if (METHOD == MVHMR_MEAN) {                    // x / V, correctly rounded (see div_const2)
-            return upk(div_const2(a, pk(-Vf, -Vf), pk(1.0f / Vf, 1.0f / Vf), Vf, Vf));
-        }
-        if (METHOD == MVHMR_MAX) { f2 r; r.x = m0; r.y = m1; return r; }
-        const f2 s = upk(S);
-        return upk(mul2(a, pk(rcp_approx(s.x), rcp_approx(s.y))));
-    }
-};
-
 // VMAX : views held in registers at once (V > VMAX walks view blocks, fusion state carried)
 // EXACT: V == VMAX — view loops are straight-line code, record layout is a compile-time constant
 // CACHE: keep the corner texels of every view across the z walk
@@ -143,7 +79,8 @@ unproject_kernel(const UnprojParams p)
     const int grp = lane >> lpv_log, chunk = lane & (nch_pass - 1);
     const int nvec = BF16 ? 2 * nch_pass : nch_pass; // float4 vectors per tile row
     const float Vf = (float)p.V;
-    const unsigned px = 1u << lpb, row = (unsigned)p.Wp << lpb;
+    // lpb < 0: planes with a padded pixel stride (see make_cell)
+    const unsigned px = lpb > 0 ? 1u << lpb : (unsigned)p.pstride, row = (unsigned)p.Wp * px;
     const int wbytes = EXACT ? VMAX * 16 : p.V * 16;
     const int rec_bytes = EXACT ? VMAX * 16 + ((VMAX + 3) & ~3) * 4 : p.rec_bytes;
 
@@ -367,8 +304,9 @@ unproject_kernel(const UnprojParams p)
 template <bool BF16>
 __global__ void __launch_bounds__(256)
 pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, int H, int W,
-            int nchunks, int Hp, int Wp, int vec)
+            int nchunks, int Hp, int Wp, int vec, int ps16)
 {
+    // ps16: 16-byte vectors from one pixel to the next (nchunks, or nchunks + 1 zero vector of padding)
     constexpr int CPT = BF16 ? 8 : 4;            // channels per 16-byte vector
     constexpr int CB = 64;                       // channels per tile
     constexpr int XB = 128;                      // pixels per tile
@@ -377,10 +315,10 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
     unsigned short *tile_h = reinterpret_cast<unsigned short *>(pack_smem);
     const int bv = blockIdx.x / Hp;
     const int y = blockIdx.x % Hp - kBorder;
-    uint4 *dst_row = packed + (size_t)blockIdx.x * Wp * nchunks;
+    uint4 *dst_row = packed + (size_t)blockIdx.x * Wp * ps16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (y < 0 || y >= H) {
-        for (int e = threadIdx.x; e < Wp * nchunks; e += blockDim.x) dst_row[e] = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = threadIdx.x; e < Wp * ps16; e += blockDim.x) dst_row[e] = make_uint4(0u, 0u, 0u, 0u);
         return;
     }
     const int CP = nchunks * CPT;
@@ -391,10 +329,12 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
         // channel in flight, four channels per warp at a time; the four border pixels of the row are
         // written separately.
         constexpr int EPV = BF16 ? 8 : 4;                              // elements per 16-byte load
-        for (int e = threadIdx.x; e < 4 * nchunks; e += blockDim.x) {
-            const int pxl = e / nchunks;
-            dst_row[(size_t)(pxl < 2 ? pxl : W + pxl) * nchunks + (e - pxl * nchunks)] = make_uint4(0u, 0u, 0u, 0u);
+        for (int e = threadIdx.x; e < 4 * ps16; e += blockDim.x) {
+            const int pxl = e / ps16;
+            dst_row[(size_t)(pxl < 2 ? pxl : W + pxl) * ps16 + (e - pxl * ps16)] = make_uint4(0u, 0u, 0u, 0u);
         }
+        if (ps16 > nchunks)                                              // the padding vector of every pixel
+            for (int e = threadIdx.x; e < W; e += blockDim.x) dst_row[(size_t)(kBorder + e) * ps16 + nchunks] = make_uint4(0u, 0u, 0u, 0u);
         for (int xs = 0; xs < W; xs += XB) {
             const int xn = min(XB, W - xs), nq = xn / EPV;
             for (int cb = 0; cb < CP; cb += CB) {
@@ -433,7 +373,7 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
                             v = make_uint4(__float_as_uint(tile_f[(k * 4 + 0) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 1) * (XB + 1) + j]),
                                            __float_as_uint(tile_f[(k * 4 + 2) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 3) * (XB + 1) + j]));
                         }
-                        dst_row[(size_t)(xs + kBorder + j) * nchunks + cb / CPT + k] = v;
+                        dst_row[(size_t)(xs + kBorder + j) * ps16 + cb / CPT + k] = v;
                     }
                 }
                 __syncthreads();
@@ -441,6 +381,8 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
         }
         return;
     }
+    if (ps16 > nchunks)
+        for (int e = threadIdx.x; e < Wp; e += blockDim.x) dst_row[(size_t)e * ps16 + nchunks] = make_uint4(0u, 0u, 0u, 0u);
     for (int x0 = -kBorder; x0 < W + kBorder; x0 += XB) {
         const int xn = min(XB, W + kBorder - x0);                      // padded pixels in this block
         for (int cb = 0; cb < CP; cb += CB) {
@@ -469,7 +411,7 @@ pack_kernel(const void *__restrict__ feats, uint4 *__restrict__ packed, int C, i
                         v = make_uint4(__float_as_uint(tile_f[(k * 4 + 0) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 1) * (XB + 1) + j]),
                                        __float_as_uint(tile_f[(k * 4 + 2) * (XB + 1) + j]), __float_as_uint(tile_f[(k * 4 + 3) * (XB + 1) + j]));
                     }
-                    dst_row[(size_t)(x0 + kBorder + j) * nchunks + cb / CPT + k] = v;
+                    dst_row[(size_t)(x0 + kBorder + j) * ps16 + cb / CPT + k] = v;
                 }
             }
             __syncthreads();
@@ -532,25 +474,33 @@ static cudaError_t launch_lpb(int method, dim3 grid, size_t smem, cudaStream_t s
     return launch_method<VMAX, EXACT, CACHE, BF16, 0>(method, grid, smem, st, p);
 }
 
-}  // namespace mvhmr
+bool staged_shape(int feat_dtype, int C)
+{
+    const int n = nchunks_of(feat_dtype, C);
+    return n == 4 || n == 8;
+}
 
-using namespace mvhmr;
+bool staged_allowed()
+{
+    // The staged kernel lost the A/B on every BASELINE config: it runs only on
+    // request, MVHMR_PATH=staged (tests, profiles); the default is the L1-gather kernel over dense planes.
+    const char *env = getenv("MVHMR_PATH");
+    return env && env[0] == 's';
+}
 
-extern "C" size_t mvhmr_packed_bytes(int feat_dtype, int BV, int C, int H, int W)
+int packed_ps16(int feat_dtype, int C)
+{
+    const int n = nchunks_of(feat_dtype, C);
+    return (staged_shape(feat_dtype, C) && staged_allowed()) ? n + 1 : n;
+}
+
+size_t packed_bytes_layout(int feat_dtype, int BV, int C, int H, int W, int ps16)
 {
     if ((feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16) || BV < 0 || C < 1 || H < 1 || W < 1) return 0;
-    return (size_t)BV * nchunks_of(feat_dtype, C) * (H + 2 * kBorder) * (W + 2 * kBorder) * sizeof(uint4);
+    return (size_t)BV * ps16 * (H + 2 * kBorder) * (W + 2 * kBorder) * sizeof(uint4);
 }
 
-extern "C" size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, int V, int C, int H, int W)
-{
-    if (feat_layout == MVHMR_LAYOUT_PACKED || feat_layout == MVHMR_LAYOUT_NHWC) return 0;
-    if (B < 0 || V < 0) return 0;
-    return mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);
-}
-
-extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *packed,
-                                   int BV, int C, int H, int W, void *stream)
+int pack_features_layout(const void *feats, int feat_dtype, void *packed, int BV, int C, int H, int W, int ps16, void *stream)
 {
     if (feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: unknown feat_dtype %d", feat_dtype);
@@ -568,10 +518,35 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     const int epv = feat_dtype == MVHMR_BF16 ? 8 : 4;
     const int vec = (W % epv == 0) && (((uintptr_t)feats & 15) == 0);
     if (feat_dtype == MVHMR_BF16)
-        pack_kernel<true><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 2) * 2, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp, vec);
+        pack_kernel<true><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 2) * 2, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp, vec, ps16);
     else
-        pack_kernel<false><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 1) * 4, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp, vec);
+        pack_kernel<false><<<(unsigned)rows, 256, (size_t)tile_rows * (128 + 1) * 4, (cudaStream_t)stream>>>(feats, (uint4 *)packed, C, H, W, nchunks, Hp, Wp, vec, ps16);
     return check_launch("pack_kernel");
+}
+
+}  // namespace mvhmr
+
+using namespace mvhmr;
+
+extern "C" size_t mvhmr_packed_bytes(int feat_dtype, int BV, int C, int H, int W)
+{
+    if ((feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16) || C < 1) return 0;
+    return packed_bytes_layout(feat_dtype, BV, C, H, W, packed_ps16(feat_dtype, C));
+}
+
+extern "C" size_t mvhmr_unproject_workspace_bytes(int feat_dtype, int feat_layout, int B, int V, int C, int H, int W)
+{
+    if (feat_layout == MVHMR_LAYOUT_PACKED || feat_layout == MVHMR_LAYOUT_NHWC) return 0;
+    if (B < 0 || V < 0) return 0;
+    return mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);
+}
+
+extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *packed,
+                                   int BV, int C, int H, int W, void *stream)
+{
+    if ((feat_dtype != MVHMR_F32 && feat_dtype != MVHMR_BF16) || C < 1)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "pack_features: unknown feat_dtype %d or bad C=%d", feat_dtype, C);
+    return pack_features_layout(feats, feat_dtype, packed, BV, C, H, W, packed_ps16(feat_dtype, C), stream);
 }
 
 static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
@@ -605,7 +580,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     if (!feats || !proj || !out || (!coord && !grid_desc)) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
     if (grid_desc && (!grid_desc->centers || !grid_desc->rot))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_grid: null centers / rot");
-    if ((long long)(H + 4) * (W + 4) * nchunks_of(feat_dtype, C) * 16 >= (1LL << 31))
+    if ((long long)(H + 4) * (W + 4) * (nchunks_of(feat_dtype, C) + 1) * 16 >= (1LL << 31))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: one padded feature map must stay below 2 GiB");
     if ((uintptr_t)proj & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: proj must be 16-byte aligned");
 
@@ -643,21 +618,30 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     if (smem > 220 * 1024)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: V=%d needs %zu bytes of shared memory", V, smem);
 
+    // Which kernel takes the call.  The staged kernel (unproject_staged.cu) handles pixels of 64 / 128
+    // bytes and exactly 4 or 8 views over the padded packed planes; the L1-gather kernel below takes
+    // everything else, and channels-last maps read in place.
+    const int ps_dense = nchunks, ps_padded = nchunks + 1;
+    const bool staged = staged_shape(feat_dtype, C) && staged_allowed() && (V == 4 || V == 8) &&
+                        feat_layout != MVHMR_LAYOUT_NHWC;
+    int ps16;                                                       // pixel stride of the planes this call reads
     const char *packed;
     if (feat_layout == MVHMR_LAYOUT_NCHW) {
-        const size_t need = mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);
+        ps16 = staged ? ps_padded : ps_dense;
+        const size_t need = mvhmr_packed_bytes(feat_dtype, B * V, C, H, W);     // sized for the larger layout
         if (!ws || ws_bytes < need)
             return fail(MVHMR_ERR_WORKSPACE, "unproject_aggregate: workspace of %zu bytes required, got %zu", need, ws_bytes);
         if ((uintptr_t)ws & 15) return fail(MVHMR_ERR_WORKSPACE, "unproject_aggregate: workspace must be 16-byte aligned");
         // only the samples of the shard window are packed
         const size_t per_sample_in = (size_t)V * C * H * W * (bf ? 2 : 4);
-        const size_t per_sample_pk = need / (size_t)B;
-        int rc = mvhmr_pack_features((const char *)feats + per_sample_in * b0, feat_dtype,
-                                     (char *)ws + per_sample_pk * b0, (b1 - b0) * V, C, H, W, stream);
+        const size_t per_sample_pk = packed_bytes_layout(feat_dtype, V, C, H, W, ps16);
+        int rc = pack_features_layout((const char *)feats + per_sample_in * b0, feat_dtype,
+                                      (char *)ws + per_sample_pk * b0, (b1 - b0) * V, C, H, W, ps16, stream);
         if (rc != MVHMR_OK) return rc;
         packed = (const char *)ws;
     } else {
         if ((uintptr_t)feats & 15) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: packed / channels-last features must be 16-byte aligned");
+        ps16 = feat_layout == MVHMR_LAYOUT_PACKED ? packed_ps16(feat_dtype, C) : ps_dense;
         if (feat_layout == MVHMR_LAYOUT_NHWC) {
             // the caller's (B,V,H,W,C) maps are gathered in place: a pixel must be a power-of-two
             // number of 16-byte vectors and the cell logic needs two texels per axis
@@ -681,9 +665,10 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     p.border = (feat_layout == MVHMR_LAYOUT_NHWC) ? 0 : kBorder;
     p.Wp = W + 2 * p.border;
     p.nchunks = nchunks;
-    p.lpb = ilog2_exact(nchunks) + 4;
-    p.plane_bytes = ((long long)(H + 2 * p.border) * p.Wp) << p.lpb;
-    if ((long long)V * p.plane_bytes + ((long long)(p.Wp + 1) << p.lpb) + 16LL * nchunks >= (1LL << 32))
+    p.pstride = ps16 * 16;
+    p.lpb = ps16 == nchunks ? ilog2_exact(nchunks) + 4 : -1;        // -1: padded pixel stride, offsets by multiplication
+    p.plane_bytes = (long long)(H + 2 * p.border) * p.Wp * p.pstride;
+    if ((long long)V * p.plane_bytes + (long long)(p.Wp + 1) * p.pstride + 16LL * nchunks >= (1LL << 32))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: the padded feature maps of one sample must stay below 4 GiB");
     p.plane32 = (unsigned)p.plane_bytes;
     p.V = V; p.VP = VP; p.C = C; p.W = W; p.H = H; p.b0 = b0; p.nb = b1 - b0;
@@ -704,6 +689,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
     p.rH = 1.0f / (float)H; p.rW = 1.0f / (float)W;
+    if (staged && ps16 == ps_padded) return launch_unproject_staged(p, bf, method, stream);
     p.nxb = (unsigned)((p.nx + kWarps - 1) / kWarps);
     const long long ntasks = (long long)p.nb * p.nseg * gy * p.nxb;
     if (ntasks > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: too many z rows in one call");
