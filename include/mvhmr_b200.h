@@ -165,6 +165,29 @@ int mvhmr_unproject_aggregate_grid(const void *feats, int feat_dtype, int feat_l
                                    long long n_origin, long long n_extent,
                                    unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
 
+/* Consumer-side output formats (the first thing the reference's
+ * consumer does with the aggregate is a 3-D conv block followed by max_pool3d(2),
+ * models/regressor.py:70-75):
+ *   MVHMR_OUT_NDHWC  out is (B, n_extent, C): a voxel's channels are contiguous — PyTorch's
+ *                    channels_last_3d memory format, what a tensor-core 3-D conv wants.  Written
+ *                    straight from the fusion registers (no shared-memory transposition);
+ *                    needs C % 4 == 0.  Same values as the default layout.
+ *   MVHMR_OUT_POOL2  out is (B, C, n_extent / 8): only the maximum of every 2x2x2 voxel block is
+ *                    written (max_pool3d(kernel 2, stride 2) of the aggregate, NaN-propagating
+ *                    like torch), the full-resolution volume never reaches memory.  Needs an even
+ *                    volume shape, windows made of whole x-plane pairs and C <= 128 (fp32).
+ * Exactly one of `coord` / `grid` is non-NULL.  All other arguments as mvhmr_unproject_aggregate. */
+#define MVHMR_OUT_NDHWC 1u
+#define MVHMR_OUT_POOL2 2u
+int mvhmr_unproject_aggregate_fmt(const void *feats, int feat_dtype, int feat_layout,
+                                  const float *proj, const float *coord, const mvhmr_grid_t *grid,
+                                  float *out, unsigned out_flags,
+                                  int B, int V, int C, int H, int W,
+                                  int gx, int gy, int gz, int method,
+                                  int b0, int b1, long long n0, long long n1,
+                                  long long n_origin, long long n_extent,
+                                  unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
+
 /* mvhmr_soft_argmax3d_strided with the voxel coordinates generated from `grid`
  * (same arithmetic as mvhmr_build_coord_volumes, so the result has the same bits
  * as building the coord volume first): with mvhmr_unproject_aggregate_grid no

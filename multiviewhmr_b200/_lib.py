@@ -15,6 +15,7 @@ OK, ERR_INVALID_ARGUMENT, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3
 SUM, MEAN, MAX, SOFTMAX = 0, 1, 2, 3
 F32, BF16 = 0, 1
 LAYOUT_NCHW, LAYOUT_PACKED, LAYOUT_NHWC = 0, 1, 2
+OUT_NDHWC, OUT_POOL2 = 1, 2
 METHODS = {"sum": SUM, "mean": MEAN, "max": MAX, "softmax": SOFTMAX}
 
 _vp, _i, _ll, _sz, _u = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_size_t, ctypes.c_uint
@@ -34,6 +35,8 @@ SIGNATURES = {
                                        _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
     "mvhmr_unproject_aggregate_grid": (_i, [_vp, _i, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                             _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
+    "mvhmr_unproject_aggregate_fmt": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _u, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                           _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
     "mvhmr_unproject_aggregate_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp]),
     "mvhmr_unproject_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mvhmr_unproject_aggregate_backward_ws": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp, _sz, _vp]),

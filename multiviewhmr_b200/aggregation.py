@@ -64,7 +64,7 @@ def pack_features(features):
 
 
 def unprojection(features, proj_matricies, coord_volumes, aggregation_method='softmax',
-                 window=None, out=None, packed=None):
+                 window=None, out=None, packed=None, output='ncdhw'):
     """Unproject V feature maps into the voxel grid and fuse over views.
 
     Reference: `models/aggregation.py:20-87`.
@@ -77,8 +77,17 @@ def unprojection(features, proj_matricies, coord_volumes, aggregation_method='so
 
     Extras (not in the reference): `window=(b0, b1, n0, n1)` computes only a
     shard of samples / flattened voxels into `out`; `packed` re-uses a
-    `pack_features` result.
+    `pack_features` result; `output` selects a consumer-side format
+    (inference only):
+      'ncdhw'             the reference's contiguous (B,C,Gx,Gy,Gz) tensor (default)
+      'channels_last_3d'  same shape and values, `torch.channels_last_3d` strides — what a
+                          tensor-core 3-D conv (`models/regressor.py:70-75`) consumes; written
+                          without the shared-memory transposition
+      'max_pool2'         `F.max_pool3d(volume, 2)` of the aggregate, (B,C,Gx/2,Gy/2,Gz/2):
+                          the full-resolution volume is never written
     """
+    if output not in _OUTPUTS:
+        raise ValueError("unprojection: output must be one of %s, got %r" % (sorted(_OUTPUTS), output))
     if aggregation_method not in _lib.METHODS:
         raise ValueError("Unknown aggregation_method: {}".format(aggregation_method))
     dev = _lib.require_cuda(features, proj_matricies, coord_volumes)
@@ -90,6 +99,9 @@ def unprojection(features, proj_matricies, coord_volumes, aggregation_method='so
         raise ValueError("shape mismatch: features %s, proj_matricies %s, coord_volumes %s"
                          % (tuple(features.shape), tuple(proj_matricies.shape), tuple(coord_volumes.shape)))
     if torch.is_grad_enabled() and features.requires_grad:
+        if output != 'ncdhw':
+            raise ValueError("unprojection: output=%r is an inference format; with autograd use the default "
+                             "layout and torch ops on the result" % output)
         if out is not None:
             raise ValueError("unprojection: `out=` cannot be combined with autograd (features.requires_grad); "
                              "use the returned tensor or call under torch.no_grad()")
@@ -104,11 +116,14 @@ def unprojection(features, proj_matricies, coord_volumes, aggregation_method='so
     gx, gy, gz = (int(v) for v in coord_volumes.shape[1:4])
     coord = coord_volumes.detach().float().contiguous()
     return _launch_unprojection(features, proj_matricies, (gx, gy, gz), aggregation_method, window, out, packed,
-                                coord=coord)
+                                coord=coord, output=output)
+
+
+_OUTPUTS = {'ncdhw': 0, 'channels_last_3d': _lib.OUT_NDHWC, 'max_pool2': _lib.OUT_POOL2}
 
 
 def _launch_unprojection(features, proj_matricies, shape, aggregation_method, window, out, packed,
-                         coord=None, grid=None):
+                         coord=None, grid=None, output='ncdhw'):
     dev = features.device
     B, V, C, H, W = features.shape
     gx, gy, gz = shape
@@ -116,11 +131,27 @@ def _launch_unprojection(features, proj_matricies, shape, aggregation_method, wi
     dt = _feat_dtype(features)
     L = _lib.load()
     proj = proj_matricies.detach().float().contiguous()
+    flags = _OUTPUTS[output]
+    if flags == _lib.OUT_POOL2:
+        if (gx | gy | gz) & 1:
+            raise ValueError("output='max_pool2' needs an even volume shape, got %s" % (shape,))
+        out_shape = (B, C, gx // 2, gy // 2, gz // 2)
+    else:
+        out_shape = (B, C, gx, gy, gz)
     if out is None:
-        out = torch.empty((B, C, gx, gy, gz), dtype=torch.float32, device=dev)
-    elif (tuple(out.shape) != (B, C, gx, gy, gz) or out.dtype != torch.float32
-          or not out.is_contiguous() or out.device != dev):
-        raise ValueError("out must be a contiguous float32 (B,C,Gx,Gy,Gz) tensor on %s" % dev)
+        if flags == _lib.OUT_NDHWC:
+            out = torch.empty((B, gx, gy, gz, C), dtype=torch.float32, device=dev).permute(0, 4, 1, 2, 3)
+        else:
+            out = torch.empty(out_shape, dtype=torch.float32, device=dev)
+    else:
+        ok = tuple(out.shape) == out_shape and out.dtype == torch.float32 and out.device == dev
+        if flags == _lib.OUT_NDHWC:
+            ok = ok and out.permute(0, 2, 3, 4, 1).is_contiguous()
+        else:
+            ok = ok and out.is_contiguous()
+        if not ok:
+            raise ValueError("out must be a float32 %s tensor on %s, %s" % (
+                out_shape, dev, "channels_last_3d" if flags == _lib.OUT_NDHWC else "contiguous"))
     b0, b1, n0, n1 = (0, B, 0, N) if window is None else (int(v) for v in window)
     with torch.cuda.device(dev):
         if packed is None and _is_channels_last(features):
@@ -139,7 +170,11 @@ def _launch_unprojection(features, proj_matricies, shape, aggregation_method, wi
                 raise ValueError("packed features do not match the shape of `features`")
         tail = (B, V, C, H, W, gx, gy, gz, _lib.METHODS[aggregation_method],
                 b0, b1, n0, n1, 0, N, _tile_hint(), ws_ptr, ws_bytes, _lib.stream_ptr(dev))
-        if grid is None:
+        if flags:
+            _lib.check(L.mvhmr_unproject_aggregate_fmt(
+                _lib.ptr(feats), dt, layout, _lib.ptr(proj), _lib.ptr(coord) if grid is None else None,
+                ctypes.byref(grid) if grid is not None else None, _lib.ptr(out), flags, *tail))
+        elif grid is None:
             _lib.check(L.mvhmr_unproject_aggregate(_lib.ptr(feats), dt, layout, _lib.ptr(proj), _lib.ptr(coord),
                                                    _lib.ptr(out), *tail))
         else:
@@ -149,7 +184,7 @@ def _launch_unprojection(features, proj_matricies, shape, aggregation_method, wi
 
 
 def unprojection_grid(features, proj_matricies, centers, rotations, volume_size, cuboid_side,
-                      aggregation_method='softmax', window=None, out=None, packed=None):
+                      aggregation_method='softmax', window=None, out=None, packed=None, output='ncdhw'):
     """`unprojection` over the cuboid grid of `models/aggregation.py:135-187` without
     materialising it: the voxel coordinates are generated inside the kernel from the
     per-sample centre and rotation (same fp32 roundings as `build_coord_volumes`, so the
@@ -166,7 +201,9 @@ def unprojection_grid(features, proj_matricies, centers, rotations, volume_size,
     if torch.is_grad_enabled() and features.requires_grad:
         coord_volumes = build_coord_volumes(centers, rotations, volume_size, cuboid_side, dev)
         return unprojection(features, proj_matricies, coord_volumes, aggregation_method,
-                            window=window, out=out, packed=packed)
+                            window=window, out=out, packed=packed, output=output)
+    if output not in _OUTPUTS:
+        raise ValueError("unprojection_grid: output must be one of %s, got %r" % (sorted(_OUTPUTS), output))
     G = int(volume_size)
     dev_buf = _grid_buffer(centers, rotations, dev)
     grid = _lib.Grid()
@@ -178,7 +215,7 @@ def unprojection_grid(features, proj_matricies, centers, rotations, volume_size,
         grid.pos[k] = float(pos)
         grid.step[k] = float(step)
     return _launch_unprojection(features, proj_matricies, (G, G, G), aggregation_method, window, out, packed,
-                                grid=grid)
+                                grid=grid, output=output)
 
 
 def _check_grid_arrays(centers, rotations, B):

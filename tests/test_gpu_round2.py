@@ -229,3 +229,94 @@ def test_grid_descriptor_arrays_are_shape_checked():
     vol = torch.zeros(2, 3, 4, 4, 4, device=DEV)
     with pytest.raises(ValueError):
         agg.soft_argmax_3d_grid(vol, good_c[:1], good_r, 2500.0)
+
+
+# ---------------------------------------------------------------- consumer-side output formats
+FMT_SHAPES = [  # B, V, C, H, W, G, bf16
+    (1, 4, 32, 24, 24, (8, 8, 32), False), (2, 8, 32, 20, 28, (6, 4, 80), False), (1, 3, 8, 12, 12, (4, 6, 10), False),
+    (1, 4, 64, 16, 16, (4, 4, 12), True), (1, 8, 64, 16, 16, (2, 6, 34), False), (2, 2, 20, 9, 11, (2, 2, 6), False),
+    (1, 4, 32, 16, 16, (6, 6, 6), True), (1, 11, 16, 10, 10, (4, 2, 8), False)]
+
+
+@pytest.mark.parametrize("shape", FMT_SHAPES)
+@pytest.mark.parametrize("method", ["sum", "mean", "max", "softmax"])
+def test_channels_last_3d_output_has_the_same_values(shape, method):
+    B, V, C, H, W, G, bf = shape
+    g = torch.Generator().manual_seed(V * 100 + C)
+    f = torch.randn(B, V, C, H, W, generator=g)
+    P = syn.make_projections(B, V, H, W, behind_views=(V - 1,) if V > 2 else ())
+    cv = (torch.rand(B, *G, 3, generator=g) - 0.5) * 2600.0
+    fd, Pd, cvd = cuda(f, P, cv)
+    if bf:
+        fd = fd.bfloat16()
+    ref = agg.unprojection(fd, Pd, cvd, method)
+    got = agg.unprojection(fd, Pd, cvd, method, output="channels_last_3d")
+    assert got.shape == ref.shape and got.is_contiguous(memory_format=torch.channels_last_3d)
+    assert torch.equal(got, ref)
+    # a window into a NaN-poisoned channels-last buffer
+    N = G[0] * G[1] * G[2]
+    out = torch.full((B, *G, C), float("nan"), device=DEV).permute(0, 4, 1, 2, 3)
+    n0, n1 = N // 3, N - 1
+    agg.unprojection(fd, Pd, cvd, method, window=(0, B, n0, n1), out=out, output="channels_last_3d")
+    flat, rflat = out.reshape(B, C, N), ref.reshape(B, C, N)
+    assert torch.equal(flat[:, :, n0:n1], rflat[:, :, n0:n1])
+    assert bool(torch.isnan(flat[:, :, :n0]).all()) and bool(torch.isnan(flat[:, :, n1:]).all())
+
+
+@pytest.mark.parametrize("shape", FMT_SHAPES)
+@pytest.mark.parametrize("method", ["sum", "mean", "max", "softmax"])
+def test_fused_max_pool_equals_pooling_the_aggregate(shape, method):
+    """output='max_pool2' == F.max_pool3d(unprojection(...), 2), bit for bit (models/regressor.py:70-75
+    pools the encoder's first block; heads that pool the aggregate itself never need it at full size)."""
+    B, V, C, H, W, G, bf = shape
+    g = torch.Generator().manual_seed(V * 100 + C + 1)
+    f = torch.randn(B, V, C, H, W, generator=g)
+    P = syn.make_projections(B, V, H, W, behind_views=(0,) if V > 2 else ())
+    cv = (torch.rand(B, *G, 3, generator=g) - 0.5) * 2600.0
+    fd, Pd, cvd = cuda(f, P, cv)
+    if bf:
+        fd = fd.bfloat16()
+    full = agg.unprojection(fd, Pd, cvd, method)
+    ref = torch.nn.functional.max_pool3d(full, 2)
+    got = agg.unprojection(fd, Pd, cvd, method, output="max_pool2")
+    assert got.shape == (B, C, G[0] // 2, G[1] // 2, G[2] // 2) and got.is_contiguous()
+    assert torch.equal(got, ref)
+    pixel = C * fd.element_size()
+    if pixel >= 16 and pixel & (pixel - 1) == 0:                     # channels-last maps gathered in place
+        fcl = fd.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+        assert torch.equal(agg.unprojection(fcl, Pd, cvd, method, output="max_pool2"), ref)
+    if G[0] >= 4:                                                    # a window of whole x-plane pairs
+        yz = G[1] * G[2]
+        out = torch.full_like(ref, float("nan"))
+        agg.unprojection(fd, Pd, cvd, method, window=(0, B, 2 * yz, G[0] * yz), out=out, output="max_pool2")
+        assert torch.equal(out[:, :, 1:], ref[:, :, 1:]) and bool(torch.isnan(out[:, :, 0]).all())
+
+
+def test_fused_max_pool_full_size_and_errors():
+    w = syn.CONFIGS["cfg2"]
+    f, P, cv, centers = syn.make_inputs(sub_workload(w, 2))
+    fd, Pd, cvd = cuda(f, P, cv)
+    full = agg.unprojection(fd, Pd, cvd, "softmax")
+    ref = torch.nn.functional.max_pool3d(full, 2)
+    assert torch.equal(agg.unprojection(fd, Pd, cvd, "softmax", output="max_pool2"), ref)
+    rots = np.stack([np.eye(3, dtype=np.float32)] * 2)
+    got = agg.unprojection_grid(fd, Pd, centers.numpy(), rots, w.G, w.cuboid_side, "softmax", output="max_pool2")
+    assert torch.equal(got, ref)
+    assert torch.equal(agg.unprojection_grid(fd, Pd, centers.numpy(), rots, w.G, w.cuboid_side, "softmax",
+                                             output="channels_last_3d"), full)
+    # NaN propagates like torch's pooling
+    fn = fd.clone()
+    fn[0, 1, 3, 40:44, 40:44] = float("nan")
+    full = agg.unprojection(fn, Pd, cvd, "sum")
+    assert bool(torch.isnan(full).any())
+    got = agg.unprojection(fn, Pd, cvd, "sum", output="max_pool2")
+    assert torch.equal(torch.isnan(got), torch.isnan(torch.nn.functional.max_pool3d(full, 2)))
+    with pytest.raises(ValueError):
+        agg.unprojection(fd, Pd, cvd[:, :, :, :63], "sum", output="max_pool2")          # odd shape
+    with pytest.raises(ValueError):
+        agg.unprojection(fd, Pd, cvd, "sum", output="ndhwc")                            # unknown name
+    with pytest.raises(ValueError):
+        agg.unprojection(fd, Pd, cvd, "sum", window=(0, 2, 5, 100), out=torch.empty_like(ref), output="max_pool2")
+    fr = fd.clone().requires_grad_(True)
+    with pytest.raises(ValueError):
+        agg.unprojection(fr, Pd, cvd, "sum", output="max_pool2")
