@@ -188,6 +188,24 @@ int mvhmr_unproject_aggregate_fmt(const void *feats, int feat_dtype, int feat_la
                                   long long n_origin, long long n_extent,
                                   unsigned tile_hint, void *ws, size_t ws_bytes, void *stream);
 
+/* Reduced-precision fast path for callers inside BASELINE.json's bf16 tolerance (1e-2 relative):
+ * the bilinear samples are taken by the texture units from fp16 copies of the maps (hardware
+ * interpolation weights are 1.8 fixed point).  Measured deviation from the reference on N(0,1)
+ * maps: about 4e-3 relative — never use it where the fp32 contract (1e-5) applies.
+ *   feats  (B,V,C,H,W) NCHW, fp32 or bf16 (|x| > 65504 saturates in fp16)
+ *   exactly one of coord / grid non-NULL; out (B,C,n_extent) fp32 as in mvhmr_unproject_aggregate
+ *   V <= 8 and V*ceil(C/4)*(H+1) <= 8192, else MVHMR_ERR_INVALID_ARGUMENT (use the exact path)
+ *   ws: mvhmr_unproject_tex_workspace_bytes(B,V,C,H,W) bytes (the fp16 planes)
+ * The library keeps a small cache of texture-object descriptors (no device memory). */
+size_t mvhmr_unproject_tex_workspace_bytes(int B, int V, int C, int H, int W);
+int mvhmr_unproject_aggregate_tex(const void *feats, int feat_dtype,
+                                  const float *proj, const float *coord, const mvhmr_grid_t *grid, float *out,
+                                  int B, int V, int C, int H, int W,
+                                  int gx, int gy, int gz, int method,
+                                  int b0, int b1, long long n0, long long n1,
+                                  long long n_origin, long long n_extent,
+                                  void *ws, size_t ws_bytes, void *stream);
+
 /* mvhmr_soft_argmax3d_strided with the voxel coordinates generated from `grid`
  * (same arithmetic as mvhmr_build_coord_volumes, so the result has the same bits
  * as building the coord volume first): with mvhmr_unproject_aggregate_grid no

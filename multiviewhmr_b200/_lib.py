@@ -37,6 +37,9 @@ SIGNATURES = {
                                             _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
     "mvhmr_unproject_aggregate_fmt": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _u, _i, _i, _i, _i, _i, _i, _i, _i, _i,
                                            _i, _i, _ll, _ll, _ll, _ll, _u, _vp, _sz, _vp]),
+    "mvhmr_unproject_tex_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mvhmr_unproject_aggregate_tex": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                           _i, _i, _ll, _ll, _ll, _ll, _vp, _sz, _vp]),
     "mvhmr_unproject_aggregate_backward": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp]),
     "mvhmr_unproject_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mvhmr_unproject_aggregate_backward_ws": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _i, _vp, _sz, _vp]),

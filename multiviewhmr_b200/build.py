@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmvhmr_b200.so")
 SOURCES = ["abi.cu", "geometry.cu", "unproject.cu", "unproject_out0.cu", "unproject_out1.cu", "unproject_out2.cu",
-           "unproject_staged.cu", "softargmax.cu", "backward.cu"]
+           "unproject_staged.cu", "unproject_tex.cu", "softargmax.cu", "backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]
 LINK_FLAGS = ["-shared", "-cudart", "static"]

@@ -339,14 +339,18 @@ static int launch_unproject_gather(const UnprojParams &p, bool bf, int method, d
 {
     const int V = p.V;
     cudaError_t e;
+    // bf16 maps hold 8 channels per lane: the generic view counts (runtime loops) run four views at a
+    // time without the texel cache there — the wider instantiations spill (ptxas: 0.4-2.4 KB).
     if (V == 4)
         e = bf ? launch_lpb<4, true, MVHMR_CACHE4, true, OUT>(method, grid, smem, st, p) : launch_lpb<4, true, MVHMR_CACHE4, false, OUT>(method, grid, smem, st, p);
-    else if (V < 4)
-        e = bf ? launch_lpb<4, false, MVHMR_CACHE4, true, OUT>(method, grid, smem, st, p) : launch_lpb<4, false, MVHMR_CACHE4, false, OUT>(method, grid, smem, st, p);
     else if (V == 8)
         e = bf ? launch_lpb<8, true, false, true, OUT>(method, grid, smem, st, p) : launch_lpb<8, true, false, false, OUT>(method, grid, smem, st, p);
+    else if (bf)
+        e = launch_lpb<4, false, false, true, OUT>(method, grid, smem, st, p);
+    else if (V < 4)
+        e = launch_lpb<4, false, MVHMR_CACHE4, false, OUT>(method, grid, smem, st, p);
     else
-        e = bf ? launch_lpb<8, false, false, true, OUT>(method, grid, smem, st, p) : launch_lpb<8, false, false, false, OUT>(method, grid, smem, st, p);
+        e = launch_lpb<8, false, false, false, OUT>(method, grid, smem, st, p);
     if (e != cudaSuccess) return fail(MVHMR_ERR_CUDA, "unproject_kernel: %s", cudaGetErrorString(e));
     return check_launch("unproject_kernel");
 }

@@ -202,8 +202,9 @@ static inline float orc_fuse32(const float *s, int V, int method)
         for (int v = 1; v < V; ++v) acc = acc + s[v];
         return method == ORC_MEAN ? acc / (float)V : acc;
     }
+    /* torch.max over the view axis propagates NaN (models/aggregation.py:76): a NaN sample wins */
     float m = s[0];
-    for (int v = 1; v < V; ++v) m = s[v] > m ? s[v] : m;
+    for (int v = 1; v < V; ++v) m = (s[v] > m || s[v] != s[v]) ? s[v] : m;
     if (method == ORC_MAX) return m;
     /* softmax over views of the sampled values themselves, then weighted sum:
      * /root/reference/models/aggregation.py:77-83 (ATen softmax = exp(x-max)/sum) */

@@ -320,3 +320,78 @@ def test_fused_max_pool_full_size_and_errors():
     fr = fd.clone().requires_grad_(True)
     with pytest.raises(ValueError):
         agg.unprojection(fr, Pd, cvd, "sum", output="max_pool2")
+
+
+# ---------------------------------------------------------------- reduced-precision texture path (bf16 tolerance)
+SPEC_TOL_BF16 = 1e-2      # north_star: aggregated volumes within 1e-2 relative with bf16 features
+
+
+def test_fast_path_cfg3_is_inside_the_bf16_tolerance(capsys):
+    """BASELINE config #3 (bf16 features, 17-joint soft-argmax) through precision='fast': the texture
+    units sample fp16 copies of the maps with 1.8 fixed-point weights.  The deviation from the
+    reference (C restatement on the bf16-rounded maps) must stay inside the stated 1e-2; what is
+    measured is printed (about 4e-3 for softmax fusion)."""
+    w = syn.CONFIGS["cfg3"]
+    f, P, cv, _ = syn.make_inputs(sub_workload(w, 2))
+    fd, Pd, cvd = cuda(f, P, cv)
+    fb = fd.bfloat16()
+    errs = {}
+    for method in ("sum", "mean", "max", "softmax"):
+        ref = oracle.unprojection(f, P, cv, method)
+        got = agg.unprojection(fb, Pd, cvd, method, precision="fast")
+        assert got.shape == ref.shape and got.dtype == torch.float32
+        errs[method] = rel_l2(got.cpu().numpy(), ref)
+        assert errs[method] < SPEC_TOL_BF16, (method, errs[method])
+        exact = agg.unprojection(fb, Pd, cvd, method)
+        assert rel_l2(exact.cpu().numpy(), ref) < OUR_TOL_SOFTMAX          # the default path stays exact
+    with capsys.disabled():
+        print("\n[fast path, cfg3 shape] rel. l2 deviation from the reference: " +
+              ", ".join("%s %.2e" % kv for kv in errs.items()))
+    # soft-argmax over the fast volume: joints move by well under a voxel (39.7 mm)
+    vol = agg.unprojection(fb, Pd, cvd, "softmax", precision="fast")
+    ex = agg.unprojection(fb, Pd, cvd, "softmax")
+    ja = agg.soft_argmax_3d(vol[:, :w.joints], cvd)
+    jb = agg.soft_argmax_3d(ex[:, :w.joints], cvd)
+    assert float((ja - jb).abs().max()) < 2.0
+
+
+@pytest.mark.parametrize("shape", [(1, 4, 32, 24, 24, (8, 8, 32), True), (2, 8, 32, 20, 28, (6, 4, 80), True),
+                                   (1, 3, 5, 12, 14, (4, 6, 10), False), (2, 2, 20, 9, 11, (2, 2, 6), True),
+                                   (1, 7, 64, 16, 16, (3, 5, 34), False)])
+@pytest.mark.parametrize("method", ["sum", "max", "softmax"])
+def test_fast_path_shapes_windows_and_invalid_views(shape, method):
+    B, V, C, H, W, G, bf = shape
+    g = torch.Generator().manual_seed(V * 10 + C)
+    f = torch.randn(B, V, C, H, W, generator=g)
+    if bf:
+        f = f.bfloat16().float()
+    P = syn.make_projections(B, V, H, W, behind_views=(V - 1,) if V > 2 else ())
+    cv = (torch.rand(B, *G, 3, generator=g) - 0.5) * 2600.0
+    ref = oracle.unprojection(f, P, cv, method)
+    fd, Pd, cvd = cuda(f, P, cv)
+    if bf:
+        fd = fd.bfloat16()
+    got = agg.unprojection(fd, Pd, cvd, method, precision="fast")
+    # max over views of noise amplifies the sampling error a little: 2e-2 on these tiny, noisy maps
+    assert rel_l2(got.cpu().numpy(), ref) < (2e-2 if method == "max" else SPEC_TOL_BF16)
+    assert np.array_equal(np.isnan(got.cpu().numpy()), np.isnan(ref))
+    N = G[0] * G[1] * G[2]
+    out = torch.full_like(got, float("nan"))
+    n0, n1 = N // 4, N - 3
+    agg.unprojection(fd, Pd, cvd, method, window=(0, B, n0, n1), out=out, precision="fast")
+    flat = out.reshape(B, C, N)
+    assert torch.equal(flat[:, :, n0:n1], got.reshape(B, C, N)[:, :, n0:n1])
+    assert bool(torch.isnan(flat[:, :, :n0]).all()) and bool(torch.isnan(flat[:, :, n1:]).all())
+
+
+def test_fast_path_rejects_what_it_cannot_do():
+    f, P, cv = cuda(torch.zeros(1, 9, 4, 8, 8), torch.zeros(1, 9, 3, 4), torch.zeros(1, 2, 2, 2, 3))
+    with pytest.raises(ValueError):
+        agg.unprojection(f, P, cv, "sum", precision="fast")                 # more than 8 views
+    with pytest.raises(ValueError):
+        agg.unprojection(f[:, :4], P[:, :4], cv, "sum", precision="fast", output="max_pool2")
+    with pytest.raises(ValueError):
+        agg.unprojection(f[:, :4], P[:, :4], cv, "sum", precision="quick")
+    fr = f[:, :4].clone().requires_grad_(True)
+    with pytest.raises(ValueError):
+        agg.unprojection(fr, P[:, :4], cv, "sum", precision="fast")

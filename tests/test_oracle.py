@@ -136,3 +136,19 @@ def test_unknown_method_raises():
     f, P, cv, _ = syn.make_inputs(syn.Workload("t", 1, 2, 4, 8, 8, 4))
     with pytest.raises(ValueError, match="Unknown aggregation_method"):
         oracle.unprojection(f, P, cv, "median")
+
+
+@pytest.mark.parametrize("method", ["sum", "mean", "max", "softmax"])
+def test_c_oracle_propagates_nan_like_torch(method):
+    """torch.max / sum / softmax over the view axis propagate NaN (models/aggregation.py:71-83);
+    the C restatement has to as well, whichever view carries it."""
+    w = syn.Workload("t", B=1, V=3, C=2, H=8, W=8, G=4)
+    f, P, cv, _ = syn.make_inputs(w, seed=7)
+    for v in range(3):
+        fn = f.clone()
+        fn[0, v, 1, 2:6, 2:6] = float("nan")
+        ref = torch_port.unprojection(fn, P, cv, method).numpy()
+        got = oracle.unprojection(fn, P, cv, method)
+        assert np.isnan(ref).any()
+        assert np.array_equal(np.isnan(got), np.isnan(ref)), (method, v)
+        assert np.allclose(got, ref, rtol=1e-6, atol=1e-6, equal_nan=True)
