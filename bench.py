@@ -374,9 +374,53 @@ def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_en
             sa_ms = e0.elapsed_time(e1) / steps
             entry["soft_argmax"] = {"joints": w.joints, "ms": sa_ms, "algorithmic_bytes": w.soft_argmax_bytes(),
                                     "roofline_frac": w.soft_argmax_bytes() / (sa_ms * 1e-3) / 1e9 / peak}
+        if w.dtype == "bf16":
+            # the opt-in reduced-precision path (texture units, fp16 maps): inside the bf16 tolerance (1e-2)
+            f, P, cv = share.dev_sets[0]
+            exact = share.step(agg, 0).clone()
+            fast = agg.unprojection(f, P, cv, w.method, precision="fast")
+            dev_rel = float((fast.double() - exact.double()).norm() / exact.double().norm())
+            del exact, fast
+            for i in range(3):
+                agg.unprojection(f, P, cv, w.method, out=share.outs[i % 2], precision="fast")
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for i in range(steps):
+                f, P, cv = share.dev_sets[i % share.n_sets]
+                agg.unprojection(f, P, cv, w.method, out=share.outs[i % 2], precision="fast")
+            e1.record(stream)
+            barrier()
+            fms = e0.elapsed_time(e1) / steps
+            entry["fast_path"] = {"ms_per_step": fms, "value": w.vcv / (fms * 1e-3) / 1e9, "unit": UNIT,
+                                  "step_frac": alg / (fms * 1e-3) / 1e9 / peak, "rel_l2_vs_exact": dev_rel,
+                                  "tolerance": 1e-2, "speedup_vs_exact_step": ms / fms,
+                                  "note": "precision='fast': tex_pack_kernel + unproject_tex_kernel (hardware bilinear filtering of fp16 texels)"}
         block[name] = entry
         del share
         torch.cuda.empty_cache()
+    return block
+
+
+def output_format_block(agg, dev, stream, barrier):
+    """Consumer-side output formats of the fused kernel at cfg2: device time over pre-packed planes."""
+    w = syn.CONFIGS["cfg2"]
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = (t.to(dev) for t in (f, P, cv))
+    packed = agg.pack_features(fd)
+    block = {}
+    for fmt in ("ncdhw", "channels_last_3d", "max_pool2"):
+        out = agg.unprojection(fd, Pd, cvd, w.method, packed=packed, output=fmt)
+        for _ in range(3):
+            agg.unprojection(fd, Pd, cvd, w.method, packed=packed, out=out, output=fmt)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(30):
+            agg.unprojection(fd, Pd, cvd, w.method, packed=packed, out=out, output=fmt)
+        e1.record(stream)
+        barrier()
+        block[fmt] = {"kernel_ms": e0.elapsed_time(e1) / 30, "output_bytes": out.numel() * 4}
     return block
 
 
@@ -507,7 +551,8 @@ def main():
             del share
             torch.cuda.empty_cache()
             line["configs"] = per_config_block(agg, dev, stream, barrier, peak, w.name, head)
-            line["extras"] = {"backward": backward_block(dev, stream, barrier, peak)}
+            line["extras"] = {"backward": backward_block(dev, stream, barrier, peak),
+                              "output_formats_cfg2": output_format_block(agg, dev, stream, barrier)}
         if world == 1 and not args.no_cpu_baseline:
             val, sec, cores, sample = cpu_reference_sample(w, steps=3, warmup=1)
             line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
