@@ -189,7 +189,7 @@ unproject_kernel(const UnprojParams p)
         // global memory (a lane group holds all channels of its voxel: one contiguous run), or, pooled
         // output, the running maximum of the 2x2x2 block in row zl / 2
         float *const ovox = p.out + ((size_t)b * p.n_extent + (size_t)(nrow - p.n_origin)) * p.C;   // out_ndhwc: first voxel of the task
-        auto emit = [&](int zl, const Fuse2<METHOD, VMAX, EXACT> *fz) {
+        auto emit = [&](int zl, const auto *fz) {
 #pragma unroll
             for (int h = 0; h < NP / 2; ++h) {
                 const f2 r0 = fz[2 * h].result(Vf), r1 = fz[2 * h + 1].result(Vf);

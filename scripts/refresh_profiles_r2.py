@@ -94,7 +94,8 @@ with open(os.path.join(PR, 'r2_microbenchmarks.txt'), 'w') as f:
                         ('tex_bench.log', 'scripts/micro/tex_bench.cu (hardware bilinear filtering of half4 texels: rate and error)'),
                         ('path1.log', 'scripts/path_bench.py (MVHMR_PATH=gather|staged, first working staged kernel, default knobs)'),
                         ('path2.log', 'scripts/path_bench.py staged only: MVHMR_STAGED_T (threads per voxel) x MVHMR_STAGED_CTAS (CTAs per SM)'),
-                        ('var1.log', 'scripts/variant_bench.py: compile-time variants of the gather kernel at V = 8 (MVHMR_TV views in registers, MVHMR_WARPS)')):
+                        ('var1.log', 'scripts/variant_bench.py: compile-time variants of the gather kernel at V = 8 (MVHMR_TV views in registers, MVHMR_WARPS)'),
+                        ('var2.log', 'scripts/variant_bench.py: two voxels in flight per lane group, views fused 1 / 2 / 4 at a time (reverted)')):
         pth = os.path.join(GO, name)
         if os.path.exists(pth):
             f.write('==== %s\n%s\n' % (title, open(pth).read()))
