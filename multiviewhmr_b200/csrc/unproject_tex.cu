@@ -73,6 +73,73 @@ tex_pack_kernel(const void *__restrict__ feats, __half *__restrict__ planes, int
     }
 }
 
+// Vector form for rows made of whole, 16-byte aligned groups of 8 (bf16) / 4 (fp32) pixels: a thread loads
+// one 16-byte run of each of the quad's four channels and writes the 8 / 4 texels as one contiguous run.
+template <bool BF16>
+__global__ void __launch_bounds__(256)
+tex_pack_vec_kernel(const void *__restrict__ feats, __half *__restrict__ planes, int C, int H, int W, int nq, size_t pitch_h,
+                    int groups_per_row, long long items)
+{
+    constexpr int PX = BF16 ? 8 : 4;                 // pixels per 16-byte load
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(it % groups_per_row);
+        const long long row = it / groups_per_row;   // (bv * nq + q) * (H + 1) + y
+        const int y = (int)(row % (H + 1));
+        const long long plane = row / (H + 1);
+        const int q = (int)(plane % nq);
+        const long long bv = plane / nq;
+        float v[4][PX];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (y < H && 4 * q + i < C) {
+                const size_t src = ((size_t)(bv * C + 4 * q + i) * H + y) * W + (size_t)g * PX;
+                u = __ldg(reinterpret_cast<const uint4 *>(BF16 ? (const void *)(static_cast<const unsigned short *>(feats) + src)
+                                                               : (const void *)(static_cast<const float *>(feats) + src)));
+            }
+            if (BF16) {
+                const unsigned w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { v[i][2 * k] = __uint_as_float(w[k] << 16); v[i][2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u); }
+            } else {
+                v[i][0] = __uint_as_float(u.x); v[i][1] = __uint_as_float(u.y); v[i][2] = __uint_as_float(u.z); v[i][3] = __uint_as_float(u.w);
+            }
+        }
+        uint2 *dst = reinterpret_cast<uint2 *>(planes + (size_t)row * pitch_h) + (size_t)g * PX;
+#pragma unroll
+        for (int k = 0; k < PX; k += 2) {            // two texels = one 16-byte store
+            unsigned h[4];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                __half2 lo = __floats2half2_rn(fminf(fmaxf(v[0][k + j], -65504.0f), 65504.0f), fminf(fmaxf(v[1][k + j], -65504.0f), 65504.0f));
+                __half2 hi = __floats2half2_rn(fminf(fmaxf(v[2][k + j], -65504.0f), 65504.0f), fminf(fmaxf(v[3][k + j], -65504.0f), 65504.0f));
+                h[2 * j] = *reinterpret_cast<unsigned *>(&lo); h[2 * j + 1] = *reinterpret_cast<unsigned *>(&hi);
+            }
+            *reinterpret_cast<uint4 *>(dst + k) = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+    }
+}
+
+// Plain (not bit-exact) sampling position for the reduced-precision path: the same formulas as
+// sample_position evaluated with ordinary FMAs and one Newton-refined reciprocal.  Differs from the exact
+// sequence by ~1e-3 px at most — two orders below the texture units' own 1/512 px weight quantisation.
+__device__ __forceinline__ f2 sample_position_fast(const float4 &P0, const float4 &P1, const float4 &P2,
+                                                    float X, float Y, float Z, const UnprojParams &p, bool &invalid)
+{
+    const float xw = fmaf(X, P0.x, fmaf(Y, P0.y, fmaf(Z, P0.z, P0.w)));
+    const float yw = fmaf(X, P1.x, fmaf(Y, P1.y, fmaf(Z, P1.z, P1.w)));
+    const float ww = fmaf(X, P2.x, fmaf(Y, P2.y, fmaf(Z, P2.z, P2.w)));
+    invalid = ww <= 0.0f;
+    const float wd = (ww == 0.0f) ? 1.0f : ww;
+    float r = rcp_approx(wd);
+    r = fmaf(r, fmaf(-wd, r, 1.0f), r);
+    // ix = ((2 (x/H - 0.5) + 1) (W-1)/2 = x (W-1)/H ; iy = y (H-1)/W
+    f2 i;
+    i.x = xw * r * (2.0f * p.sx * p.rH);
+    i.y = yw * r * (2.0f * p.sy * p.rW);
+    return i;
+}
+
 // EXACT: V == VMAX (no per-view guards); FULLC: C % 4 == 0 (no per-channel guards)
 template <int VMAX, int METHOD, bool EXACT, bool FULLC>
 __global__ void __launch_bounds__(kTexThreads)
@@ -123,7 +190,7 @@ unproject_tex_kernel(const TexParams q)
         if (EXACT || v < p.V) {
             const float4 P0 = __ldg(Pb + 3 * v), P1 = __ldg(Pb + 3 * v + 1), P2 = __ldg(Pb + 3 * v + 2);
             bool invalid;
-            const f2 i = sample_position(P0, P1, P2, X, Y, Z, p, invalid);
+            const f2 i = sample_position_fast(P0, P1, P2, X, Y, Z, p, invalid);
             const bool finite = fabsf(i.x) < INFINITY && fabsf(i.y) < INFINITY;
             nanpos = nanpos || (!finite && !invalid);
             // rows beyond the plane contribute nothing: clamp onto the zero rows around it.  depth <= 0
@@ -257,7 +324,14 @@ extern "C" int mvhmr_unproject_aggregate_tex(const void *feats, int feat_dtype,
         if (blocks > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_tex: too many rows");
         const void *src = (const char *)feats + in_sample * b0;
         __half *dst = (__half *)(planes + sample_bytes * b0);
-        if (bf) tex_pack_kernel<true><<<(unsigned)blocks, dim3(32, 8), 0, st>>>(src, dst, C, H, W, nq, pitch / 2);
+        const int px = bf ? 8 : 4;
+        if (W % px == 0 && ((uintptr_t)src & 15) == 0) {
+            const int gpr = W / px;
+            const long long items = (long long)(b1 - b0) * rows_per_sample * gpr;
+            const unsigned grid = (unsigned)((items + 255) / 256 < 148LL * 16 ? (items + 255) / 256 : 148LL * 16);
+            if (bf) tex_pack_vec_kernel<true><<<grid, 256, 0, st>>>(src, dst, C, H, W, nq, pitch / 2, gpr, items);
+            else tex_pack_vec_kernel<false><<<grid, 256, 0, st>>>(src, dst, C, H, W, nq, pitch / 2, gpr, items);
+        } else if (bf) tex_pack_kernel<true><<<(unsigned)blocks, dim3(32, 8), 0, st>>>(src, dst, C, H, W, nq, pitch / 2);
         else tex_pack_kernel<false><<<(unsigned)blocks, dim3(32, 8), 0, st>>>(src, dst, C, H, W, nq, pitch / 2);
         int rc = check_launch("tex_pack_kernel");
         if (rc != MVHMR_OK) return rc;
