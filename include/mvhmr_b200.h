@@ -272,6 +272,28 @@ int mvhmr_soft_argmax3d_partials(const float *vol, const float *coord, float *pa
  * into out (B,J,3). */
 int mvhmr_soft_argmax3d_finalize(const float *partials, float *out, int B, int J, int S, void *stream);
 
+/* ---- fused unproject + aggregate + 3-D soft-argmax ---------------------------- */
+/* BASELINE.json's target path in ONE kernel: mvhmr_unproject_aggregate (models/aggregation.py:20-87)
+ * whose warps, before a task's tile leaves shared memory, also fold its voxels into online-softmax
+ * records of the leading J channels (lane <-> joint; formula: see "3-D soft-argmax" above), merged by
+ * mvhmr_soft_argmax3d_finalize on the same stream.  The aggregate is never re-read from memory.
+ *   out     (B,C,N) fp32 as in mvhmr_unproject_aggregate (same bits) — or NULL: heads that only need
+ *           the joints skip the B*C*N*4-byte write altogether
+ *   joints  (B,J,3) fp32, 1 <= J <= min(32, C)
+ *   exactly one of coord / grid non-NULL (the coordinates the softmax expectation is taken over are
+ *   the voxel centres the kernel projects)
+ *   ws      as for mvhmr_unproject_aggregate;  sa_ws: mvhmr_unproject_softargmax_workspace_bytes(B,J)
+ * joints agree with mvhmr_soft_argmax3d over the stored volume to fp32 summation-order noise
+ * (<= 1e-5 * max|coord|, the contract of the two-kernel path). */
+size_t mvhmr_unproject_softargmax_workspace_bytes(int B, int J);
+int mvhmr_unproject_aggregate_softargmax(const void *feats, int feat_dtype, int feat_layout,
+                                         const float *proj, const float *coord, const mvhmr_grid_t *grid,
+                                         float *out, float *joints, int J,
+                                         int B, int V, int C, int H, int W,
+                                         int gx, int gy, int gz, int method,
+                                         unsigned tile_hint, void *ws, size_t ws_bytes,
+                                         void *sa_ws, size_t sa_ws_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,9 @@ SIGNATURES = {
     "mvhmr_soft_argmax3d_grid": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp, _sz, _vp]),
     "mvhmr_soft_argmax3d_partials": (_i, [_vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _vp]),
     "mvhmr_soft_argmax3d_finalize": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "mvhmr_unproject_softargmax_workspace_bytes": (_sz, [_i, _i]),
+    "mvhmr_unproject_aggregate_softargmax": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i,
+                                                  _i, _u, _vp, _sz, _vp, _sz, _vp]),
 }
 
 

@@ -396,6 +396,79 @@ def soft_argmax_3d_grid(volumes, centers, rotations, cuboid_side):
     return out
 
 
+def unprojection_soft_argmax(features, proj_matricies, coord_volumes, joints, aggregation_method='softmax',
+                             store_volume=True, packed=None, grid=None):
+    """BASELINE.json's target path in one kernel: `unprojection` (reference `models/aggregation.py:20-87`)
+    fused with the 3-D soft-argmax of the leading `joints` channels (`soft_argmax_3d`).  The warps fold
+    every tile of the aggregate into online-softmax records before it leaves shared memory, so the
+    volume is never re-read — and with `store_volume=False` never written either.
+
+      features (B,V,C,H,W) fp32 / bf16, proj_matricies (B,V,3,4), coord_volumes (B,Gx,Gy,Gz,3)
+      joints   1 <= J <= min(32, C)
+    Returns (volume (B,C,Gx,Gy,Gz) or None, joints_3d (B,J,3)).  The volume has the bits `unprojection`
+    gives; the joints agree with `soft_argmax_3d(volume[:, :J], coord_volumes)` to fp32 summation noise.
+    `grid=(centers, rotations, volume_size, cuboid_side)` replaces `coord_volumes` (pass None) by the
+    generated cuboid grid, as `unprojection_grid` does.  Inference only (no autograd)."""
+    if aggregation_method not in _lib.METHODS:
+        raise ValueError("Unknown aggregation_method: {}".format(aggregation_method))
+    if (coord_volumes is None) == (grid is None):
+        raise ValueError("unprojection_soft_argmax: give either coord_volumes or grid=(centers, rotations, volume_size, cuboid_side)")
+    dev = _lib.require_cuda(features, proj_matricies) if coord_volumes is None else _lib.require_cuda(features, proj_matricies, coord_volumes)
+    if features.dim() != 5 or tuple(proj_matricies.shape) != (features.shape[0], features.shape[1], 3, 4):
+        raise ValueError("expected features (B,V,C,H,W) and proj_matricies (B,V,3,4), got %s and %s"
+                         % (tuple(features.shape), tuple(proj_matricies.shape)))
+    if torch.is_grad_enabled() and features.requires_grad:
+        raise ValueError("unprojection_soft_argmax is an inference path; with autograd use unprojection() and torch ops")
+    B, V, C, H, W = features.shape
+    J = int(joints)
+    if not 1 <= J <= min(32, C):
+        raise ValueError("unprojection_soft_argmax: joints=%d must be in [1, min(32, C=%d)]" % (J, C))
+    L = _lib.load()
+    dt = _feat_dtype(features)
+    grid_desc, coord = None, None
+    if grid is not None:
+        centers, rotations, volume_size, cuboid_side = grid
+        _check_grid_arrays(centers, rotations, B)
+        G = int(volume_size)
+        gx = gy = gz = G
+        dev_buf = _grid_buffer(centers, rotations, dev)
+        grid_desc = _lib.Grid()
+        grid_desc.centers = dev_buf.data_ptr()
+        grid_desc.rot = dev_buf.data_ptr() + B * 3 * 4
+        for k in range(3):
+            grid_desc.pos[k] = float(np.float32(0.0 - cuboid_side / 2))
+            grid_desc.step[k] = float(np.float32(cuboid_side / (G - 1)))
+    else:
+        if coord_volumes.dim() != 5 or coord_volumes.shape[-1] != 3 or coord_volumes.shape[0] != B:
+            raise ValueError("expected coord_volumes (B,Gx,Gy,Gz,3), got %s" % (tuple(coord_volumes.shape),))
+        gx, gy, gz = (int(v) for v in coord_volumes.shape[1:4])
+        coord = coord_volumes.detach().float().contiguous()
+    proj = proj_matricies.detach().float().contiguous()
+    volume = torch.empty((B, C, gx, gy, gz), dtype=torch.float32, device=dev) if store_volume else None
+    joints_3d = torch.empty((B, J, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        if packed is None and _is_channels_last(features):
+            feats, layout, ws_bytes, ws_ptr = features.detach(), _lib.LAYOUT_NHWC, 0, None
+        elif packed is None:
+            feats, layout = features.detach().contiguous(), _lib.LAYOUT_NCHW
+            ws_bytes = L.mvhmr_unproject_workspace_bytes(dt, layout, B, V, C, H, W)
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            ws_ptr = _lib.ptr(ws)
+        else:
+            feats, layout, ws_bytes, ws_ptr = packed, _lib.LAYOUT_PACKED, 0, None
+            if packed.numel() != L.mvhmr_packed_bytes(dt, B * V, C, H, W):
+                raise ValueError("packed features do not match the shape of `features`")
+        sa_bytes = L.mvhmr_unproject_softargmax_workspace_bytes(B, J)
+        sa_ws = torch.empty(max(sa_bytes, 4), dtype=torch.uint8, device=dev)
+        _lib.check(L.mvhmr_unproject_aggregate_softargmax(
+            _lib.ptr(feats), dt, layout, _lib.ptr(proj), _lib.ptr(coord) if coord is not None else None,
+            ctypes.byref(grid_desc) if grid_desc is not None else None,
+            _lib.ptr(volume) if volume is not None else None, _lib.ptr(joints_3d), J,
+            B, V, C, H, W, gx, gy, gz, _lib.METHODS[aggregation_method], _tile_hint(), ws_ptr, ws_bytes,
+            _lib.ptr(sa_ws), sa_bytes, _lib.stream_ptr(dev)))
+    return volume, joints_3d
+
+
 def soft_argmax_3d_records(volumes, coord_volumes):
     """Shard form of `soft_argmax_3d`: online-softmax records (B,J,S,5) =
     (max, sum e, sum e*x, sum e*y, sum e*z) over the voxels of the tensors

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libmvhmr_b200.so")
-SOURCES = ["abi.cu", "geometry.cu", "unproject.cu", "unproject_out0.cu", "unproject_out1.cu", "unproject_out2.cu",
+SOURCES = ["abi.cu", "geometry.cu", "unproject.cu", "unproject_out0.cu", "unproject_out1.cu", "unproject_out2.cu", "unproject_out3.cu",
            "unproject_staged.cu", "unproject_tex.cu", "softargmax.cu", "backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2"]

@@ -270,7 +270,8 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
                           int gx, int gy, int gz, int method,
                           int b0, int b1, long long n0, long long n1,
                           long long n_origin, long long n_extent,
-                          unsigned tile_hint, void *ws, size_t ws_bytes, void *stream)
+                          unsigned tile_hint, void *ws, size_t ws_bytes, void *stream,
+                          int sa_J = 0, float *sa_rec = nullptr, size_t sa_rec_bytes = 0)
 {
     if (method < MVHMR_SUM || method > MVHMR_SOFTMAX)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "Unknown aggregation_method: %d", method);
@@ -290,7 +291,8 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: voxels [%lld,%lld) not inside the buffers' range [%lld,%lld)",
                     n0, n1, n_origin, n_origin + n_extent);
     const bool ndhwc = out_flags & MVHMR_OUT_NDHWC, pool = out_flags & MVHMR_OUT_POOL2;
-    if (out_flags & ~(unsigned)(MVHMR_OUT_NDHWC | MVHMR_OUT_POOL2) || (ndhwc && pool))
+    const bool sa = sa_J > 0;                                       // fused 3-D soft-argmax records (out may be NULL)
+    if (out_flags & ~(unsigned)(MVHMR_OUT_NDHWC | MVHMR_OUT_POOL2) || (ndhwc && pool) || (sa && out_flags))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: unsupported out_flags 0x%x", out_flags);
     if (ndhwc && (C % 4 != 0 || ((uintptr_t)out & 15)))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: channels-last-3D output needs C %% 4 == 0 and a 16-byte aligned buffer");
@@ -306,7 +308,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     if (tile_hint > (unsigned)kLzMax)
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: tile_hint %u (z-segment length) must be <= %d", tile_hint, kLzMax);
     if (b0 == b1 || n0 == n1) return MVHMR_OK;
-    if (!feats || !proj || !out || (!coord && !grid_desc)) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
+    if (!feats || !proj || (!out && !sa) || (!coord && !grid_desc)) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: null pointer");
     if (grid_desc && (!grid_desc->centers || !grid_desc->rot))
         return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_grid: null centers / rot");
     if ((long long)(H + 4) * (W + 4) * (nchunks_of(feat_dtype, C) + 1) * 16 >= (1LL << 31))
@@ -344,7 +346,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     size_t smem;
     for (;;) {                                                      // a hint that does not fit is shortened
         off_tile = (lz * rec_bytes + (32 / nch_pass) * 16 + 15) & ~15;   // + per-group skew
-        warp_smem = off_tile + lz * nvec * 16;
+        warp_smem = off_tile + lz * nvec * 16 + (sa ? kLzMax * 16 : 0);  // + the task's voxel coordinates
         smem = (size_t)warp_smem * kWarps;
         if (smem <= 160 * 1024 || lz == 1 || (pool && lz == 2)) break;
         lz = (lz + 1) / 2;
@@ -426,6 +428,8 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         p.magic_last = (65536u + steps_last - 1) / steps_last;
     }
     p.warp_smem = warp_smem; p.rec_bytes = rec_bytes; p.off_tile = off_tile;
+    p.off_xyz = off_tile + lz * nvec * 16;
+    p.sa_J = sa_J; p.sa_rec = sa_rec;
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
     p.rH = 1.0f / (float)H; p.rW = 1.0f / (float)W;
@@ -445,6 +449,16 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     const unsigned nchunk = (unsigned)((ntasks + p.ychunk - 1) / p.ychunk);
     const dim3 grid(nchunk < resident ? nchunk : resident);
     const unsigned g = grid.x;
+    if (sa) {
+        // one record per (sample, joint, CTA, warp); slots a warp never reaches stay zero (= empty for the merge)
+        const size_t need = (size_t)B * sa_J * g * kWarps * 5 * sizeof(float);
+        if (!sa_rec || sa_rec_bytes < need)
+            return fail(MVHMR_ERR_WORKSPACE, "unproject_aggregate_softargmax: record workspace of %zu bytes required, got %zu", need, sa_rec_bytes);
+        cudaError_t e = cudaMemsetAsync(sa_rec, 0, need, st);
+        if (e != cudaSuccess) return fail(MVHMR_ERR_CUDA, "unproject_aggregate_softargmax: memset: %s", cudaGetErrorString(e));
+        int rc = launch_unproject_gather_out3(p, bf, method, g, smem, stream);
+        return rc != MVHMR_OK ? rc : (int)(g * kWarps);             // > 0: record slots per (sample, joint)
+    }
     if (ndhwc) return launch_unproject_gather_out1(p, bf, method, g, smem, stream);
     if (pool) return launch_unproject_gather_out2(p, bf, method, g, smem, stream);
     return launch_unproject_gather_out0(p, bf, method, g, smem, stream);
@@ -489,6 +503,41 @@ extern "C" int mvhmr_unproject_aggregate_fmt(const void *feats, int feat_dtype, 
     if (!coord && !grid) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_fmt: give a coord volume or a grid descriptor");
     return unproject_impl(feats, feat_dtype, feat_layout, proj, coord, coord ? nullptr : grid, out, out_flags, B, V, C, H, W, gx, gy, gz, method,
                           b0, b1, n0, n1, n_origin, n_extent, tile_hint, ws, ws_bytes, stream);
+}
+
+static int sm_count()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
+extern "C" size_t mvhmr_unproject_softargmax_workspace_bytes(int B, int J)
+{
+    if (B < 0 || J < 0) return 0;
+    return (size_t)B * J * sm_count() * MVHMR_MINBLOCKS * kWarps * 5 * sizeof(float);
+}
+
+extern "C" int mvhmr_unproject_aggregate_softargmax(const void *feats, int feat_dtype, int feat_layout,
+                                                    const float *proj, const float *coord, const mvhmr_grid_t *grid,
+                                                    float *out, float *joints, int J,
+                                                    int B, int V, int C, int H, int W,
+                                                    int gx, int gy, int gz, int method,
+                                                    unsigned tile_hint, void *ws, size_t ws_bytes,
+                                                    void *sa_ws, size_t sa_ws_bytes, void *stream)
+{
+    if (!coord && !grid) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_softargmax: give a coord volume or a grid descriptor");
+    if (J < 1 || J > 32 || J > C)
+        return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_softargmax: J=%d must be in [1, min(32, C=%d)]", J, C);
+    if (B > 0 && !joints) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_softargmax: null joints pointer");
+    if (B == 0) return MVHMR_OK;
+    const long long N = (long long)gx * gy * gz;
+    const int slots = unproject_impl(feats, feat_dtype, feat_layout, proj, coord, coord ? nullptr : grid, out, 0u, B, V, C, H, W,
+                                     gx, gy, gz, method, 0, B, 0, N, 0, N, tile_hint, ws, ws_bytes, stream,
+                                     J, (float *)sa_ws, sa_ws_bytes);
+    if (slots <= 0) return slots < 0 ? slots : fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_softargmax: empty volume");
+    return mvhmr_soft_argmax3d_finalize((const float *)sa_ws, joints, B, J, slots, stream);
 }
 
 extern "C" int mvhmr_selftest_division(float d, unsigned long long *mismatches, void *stream)

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <cfloat>
 #include "mvhmr_common.cuh"
 #include "unproject_device.cuh"
 
@@ -30,7 +31,9 @@ constexpr int kLzMax = 32;                // voxels of one warp task (z segment)
 // CACHE: keep the corner texels of every view across the z walk
 // LPB  : log2(pixel bytes) as a compile-time constant (0 = take it from the parameters), so that
 //        the second texel of a row is an immediate offset and offsets shift by an immediate
-// OUT  : output format — 0 (B,C,N) as the reference, 1 channels-last-3D (B,N,C), 2 fused max_pool3d(2)
+// OUT  : output format — 0 (B,C,N) as the reference, 1 channels-last-3D (B,N,C), 2 fused max_pool3d(2),
+//        3 fused 3-D soft-argmax: (B,C,N) as format 0 (or no volume at all, p.out == NULL) plus online-softmax
+//        records (max, sum e, sum e*x, sum e*y, sum e*z) of the leading p.sa_J channels per (sample, warp)
 //
 // Grid: x = blocks of kWarps consecutive x planes, y = voxel row y, z = sample * nseg + z segment.
 // One warp = one task = one z segment (<= 32 voxels) of one (sample, x, y) row; the warps of a
@@ -61,6 +64,20 @@ unproject_kernel(const UnprojParams p)
     const int wbytes = EXACT ? VMAX * 16 : p.V * 16;
     const int rec_bytes = EXACT ? VMAX * 16 + ((VMAX + 3) & ~3) * 4 : p.rec_bytes;
 
+    // OUT == 3: lane <-> joint (channel) for the whole launch.  The lane keeps ONE online-softmax record
+    // over every voxel its warp produces for the current sample; it is flushed when the warp moves on
+    // to another sample (tasks are dealt sample-major, so at most once per sample) and at the end.
+    float4 *sa_xyz = reinterpret_cast<float4 *>(recs + p.off_xyz);   // [32] coordinates of the task's voxels
+    float sa_m = -FLT_MAX, sa_S = 0.0f, sa_X = 0.0f, sa_Y = 0.0f, sa_Z = 0.0f;
+    int sa_b = -1;
+    auto sa_flush = [&]() {
+        if (sa_b >= 0 && lane < p.sa_J) {
+            float *o = p.sa_rec + (((size_t)sa_b * p.sa_J + lane) * ((size_t)gridDim.x * kWarps) + (size_t)blockIdx.x * kWarps + warp) * 5;
+            o[0] = sa_m; o[1] = sa_S; o[2] = sa_X; o[3] = sa_Y; o[4] = sa_Z;
+        }
+        sa_m = -FLT_MAX; sa_S = sa_X = sa_Y = sa_Z = 0.0f;
+    };
+
     // Persistent CTAs.  A CTA task = kWarps consecutive x planes of one (sample, z segment, y)
     // row, one plane per warp: their projections overlap almost completely in every view, so the
     // CTA's texel footprint stays L1-resident.  Warps are never synchronised with each other and
@@ -84,6 +101,7 @@ unproject_kernel(const UnprojParams p)
     for (; ct < ct_end; ++ct, next_task()) {
     const int xi = (int)xb * kWarps + warp;
     if (xi >= p.tnx) continue;                       // padding of the last x block
+    if (OUT == 3 && b != sa_b) { sa_flush(); sa_b = b; }
     const int z0 = seg * p.lz;
     const int zn = min(p.lz, p.gz - z0);             // voxels in this segment (<= 32)
     // pool: every lane group's run starts and ends on an even z, so a 2-voxel pair never straddles groups
@@ -116,6 +134,7 @@ unproject_kernel(const UnprojParams p)
             Y = __fadd_rn(rot_row(__ldg(R + 3), __ldg(R + 4), __ldg(R + 5), d0, d1, d2), c1);
             Z = __fadd_rn(rot_row(__ldg(R + 6), __ldg(R + 7), __ldg(R + 8), d0, d1, d2), c2);
         }
+        if (OUT == 3) sa_xyz[lane] = make_float4(X, Y, Z, 0.0f);
         // lane / steps by multiplication (exact for lane < 32, steps <= 32)
         const unsigned g_of_lane = ((unsigned)lane * (zn == p.lz ? p.magic_full : p.magic_last)) >> 16;
         unsigned char *rec = recs + lane * rec_bytes + g_of_lane * 16;
@@ -264,8 +283,59 @@ unproject_kernel(const UnprojParams p)
             }
         }
         __syncwarp();
+        // ---- fused 3-D soft-argmax: lane <-> joint, the task's voxels one after the other ----
+        // Row z of the tile holds all channels of voxel z: the 32 lanes read 32 different words of one
+        // row (conflict-free whatever the swizzle), the voxel's coordinates are one broadcast read.
+        // Two straight-line passes: the task's max first (the running sums are rescaled once per task,
+        // without a branch), then exp(h - m) and the four sums.  (The fused entry point has no shard
+        // window: every voxel of the task counts.)
+        if (OUT == 3 && cb == 0) {
+            const int c = min(lane, 4 * nvec - 1);
+            const float *tf = reinterpret_cast<const float *>(tile) + (c & 3);
+            const int cv = c >> 2;
+            constexpr int NVC = LPB ? (BF16 ? 2 : 1) * ((1 << LPB) / 16 < kVecPass ? (1 << LPB) / 16 : kVecPass) : 0;   // nvec, when known
+            constexpr int PER = NVC < 32 ? NVC : 32;                 // period of the row swizzle within a task
+            float mt = -FLT_MAX;
+            if (LPB != 0 && zn == kLzMax) {
+                // full segment, compile-time row size: rows z and z + PER share their swizzle, so the lane's
+                // word offset is computed PER times and every read carries an immediate offset
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const float *t = tf + ((cv ^ k) << 2);
+#pragma unroll
+                    for (int z = k; z < kLzMax; z += PER) mt = fmaxf(mt, t[z * NVC * 4]);
+                }
+            } else {
+#pragma unroll 4
+                for (int z = 0; z < zn; ++z) mt = fmaxf(mt, tf[(z * nvec + (cv ^ (z & (nvec - 1)))) << 2]);
+            }
+            const float mn = fmaxf(sa_m, mt);
+            const float r = ex2_approx((sa_m - mn) * kLog2e);        // 1 if the max stands, 0 for the first task
+            sa_S *= r; sa_X *= r; sa_Y *= r; sa_Z *= r;
+            sa_m = mn;
+            const float nm = -mn * kLog2e;
+            auto absorb_voxel = [&](float h, int z) {
+                const float4 xyz = sa_xyz[z];
+                const float e = ex2_approx(__fmaf_rn(h, kLog2e, nm));
+                sa_S += e;
+                sa_X = __fmaf_rn(e, xyz.x, sa_X);
+                sa_Y = __fmaf_rn(e, xyz.y, sa_Y);
+                sa_Z = __fmaf_rn(e, xyz.z, sa_Z);
+            };
+            if (LPB != 0 && zn == kLzMax) {
+#pragma unroll
+                for (int k = 0; k < PER; ++k) {
+                    const float *t = tf + ((cv ^ k) << 2);
+#pragma unroll
+                    for (int z = k; z < kLzMax; z += PER) absorb_voxel(t[z * NVC * 4], z);
+                }
+            } else {
+#pragma unroll 4
+                for (int z = 0; z < zn; ++z) absorb_voxel(tf[(z * nvec + (cv ^ (z & (nvec - 1)))) << 2], z);
+            }
+        }
         // ---- read out: lane <-> voxel, one coalesced 128-byte store per channel ----
-        if (OUT != 1 && (OUT != 2 || sub == 3)) {
+        if (OUT != 1 && (OUT != 2 || sub == 3) && (OUT != 3 || p.out != nullptr)) {
             const int c_base = (BF16 ? 8 : 4) * cb;
             const bool mine_o = OUT == 2 ? lane < (zn >> 1) : mine;
             const int zr = mine_o ? lane : 0;
@@ -297,6 +367,7 @@ unproject_kernel(const UnprojParams p)
     }   // sub-rows of a pooled task (the task body)
     }   // tasks of one chunk
     }   // persistent chunk loop
+    if (OUT == 3) sa_flush();
 }
 
 template <int VMAX, bool EXACT, bool CACHE, bool BF16, int LPB, int OUT>
