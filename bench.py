@@ -374,6 +374,32 @@ def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_en
             sa_ms = e0.elapsed_time(e1) / steps
             entry["soft_argmax"] = {"joints": w.joints, "ms": sa_ms, "algorithmic_bytes": w.soft_argmax_bytes(),
                                     "roofline_frac": w.soft_argmax_bytes() / (sa_ms * 1e-3) / 1e9 / peak}
+            # BASELINE.json's target path as ONE kernel: unproject + aggregate + soft-argmax
+            # (mvhmr_unproject_aggregate_softargmax), with and without the volume store
+            fused = {"two_kernel_step_ms": ms + sa_ms}
+            two = agg.soft_argmax_3d(vol[:, :w.joints], cv)
+            for label, store in (("volume_stored", True), ("joints_only", False)):
+                for i in range(3):
+                    f, P, cv = share.dev_sets[i % share.n_sets]
+                    j = agg.unprojection_soft_argmax(f, P, cv, w.joints, w.method, store_volume=store)[1]
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                for i in range(steps):
+                    f, P, cv = share.dev_sets[i % share.n_sets]
+                    agg.unprojection_soft_argmax(f, P, cv, w.joints, w.method, store_volume=store)
+                e1.record(stream)
+                barrier()
+                fms = e0.elapsed_time(e1) / steps
+                bytes_ = alg if store else alg - w.B * w.C * w.G ** 3 * 4
+                fused[label] = {"ms_per_step": fms, "value": w.vcv / (fms * 1e-3) / 1e9, "unit": UNIT,
+                                "algorithmic_bytes": bytes_, "step_frac": bytes_ / (fms * 1e-3) / 1e9 / peak}
+            f, P, cv = share.dev_sets[0]
+            j = agg.unprojection_soft_argmax(f, P, cv, w.joints, w.method, store_volume=False)[1]
+            fused["max_abs_diff_vs_two_kernel_mm"] = float((j - two).abs().max())
+            fused["note"] = ("pack + ONE fused kernel + record merge; joints_only never writes or re-reads the volume "
+                             "(its roofline numerator drops the B*C*G^3*4 output bytes)")
+            entry["fused_soft_argmax"] = fused
         if w.dtype == "bf16":
             # the opt-in reduced-precision path (texture units, fp16 maps): inside the bf16 tolerance (1e-2)
             f, P, cv = share.dev_sets[0]

@@ -13,7 +13,9 @@ module names.
 """
 from . import aggregation, multiview, volumetric  # noqa: F401
 from .aggregation import (VolumeGenerator, build_coord_volumes, build_volume_generator, pack_features,  # noqa: F401
-                          soft_argmax_3d, soft_argmax_3d_grid, unprojection, unprojection_grid)
+                          soft_argmax_3d, soft_argmax_3d_grid, unprojection, unprojection_grid,
+                          unprojection_soft_argmax)
 
 __all__ = ["aggregation", "multiview", "volumetric", "unprojection", "unprojection_grid", "VolumeGenerator",
-           "build_volume_generator", "build_coord_volumes", "soft_argmax_3d", "soft_argmax_3d_grid", "pack_features"]
+           "build_volume_generator", "build_coord_volumes", "soft_argmax_3d", "soft_argmax_3d_grid", "pack_features",
+           "unprojection_soft_argmax"]
