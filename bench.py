@@ -212,6 +212,15 @@ class RankShare:
             self.host_sets.append((f, P, centers.numpy()))
             self.dev_sets.append(tuple(t.to(dev) for t in (f, P, cv)))
         self.outs = [torch.empty((self.nb, w.C, w.G, w.G, w.G), dtype=torch.float32, device=dev) for _ in range(2)]
+        # the packed-plane workspace of a step, allocated once (two, so that the pack of step i+1 never waits
+        # for a reader of step i in the end-to-end pipeline)
+        self.packs = [None, None]
+
+    def pack(self, agg, f, i):
+        if self.packs[i % 2] is None:
+            self.packs[i % 2] = agg.pack_features(f)
+            return self.packs[i % 2]
+        return agg.pack_features(f, out=self.packs[i % 2])
 
     def local_windows(self):
         gy = gz = self.w.G
@@ -226,7 +235,7 @@ class RankShare:
         """pack + fused kernel(s) over this rank's windows; returns the output buffer."""
         f, P, cv = inputs if inputs is not None else self.dev_sets[i % self.n_sets]
         out = self.outs[i % 2] if out is None else out
-        packed = agg.pack_features(f)
+        packed = self.pack(agg, f, i)
         for win in self.local_windows():
             agg.unprojection(f, P, cv, self.w.method, window=win, out=out, packed=packed)
         return out
@@ -246,7 +255,7 @@ def time_device_resident(agg, share, steps, warmup, stream, barrier, sampler=Non
         for i in range(steps):
             f, P, cv = share.dev_sets[i % share.n_sets]
             out = share.outs[i % 2]
-            packed = agg.pack_features(f)
+            packed = share.pack(agg, f, i)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             for win in share.local_windows():
@@ -344,6 +353,41 @@ def time_e2e(agg, share, steps, stream, barrier, dev, full_d2h, sampler):
     return sorted(reps)[1], reps, h2d, d2h
 
 
+def graph_replay_ms(share, agg, steps, stream, barrier, body=None):
+    """The step (pack + fused kernel, or `body`) captured ONCE per rotating input set into a CUDA graph and
+    replayed: the library's calls are capturable (no allocation, no host sync), so the small configs —
+    whose eager loop is bound by ~0.1 ms of Python / ctypes per call, not by the GPU — are timed as the
+    device executes them.  Returns ms per step, or None if capture is refused."""
+    try:
+        graphs = []
+        for k in range(share.n_sets):
+            f, P, cv = share.dev_sets[k]
+            out = share.outs[k % 2]
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                if body is None:
+                    agg.unprojection(f, P, cv, share.w.method, out=out, packed=share.pack(agg, f, k))
+                else:
+                    body(f, P, cv, out)
+            graphs.append(g)
+        for g in graphs:
+            g.replay()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(steps):
+            graphs[i % len(graphs)].replay()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        del graphs
+        return ms
+    except Exception as exc:                      # noqa: BLE001 — a refused capture must not cost the bench line
+        sys.stderr.write("graph capture refused: %r\n" % (exc,))
+        torch.cuda.synchronize()
+        return None
+
+
 def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_entry):
     """cfg1..cfg5 device-resident on one GPU: pack + fused kernel (cfg3: + soft-argmax)."""
     block = {}
@@ -359,6 +403,12 @@ def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_en
         entry = {"workload": describe(w), "ms_per_step": ms, "kernel_ms": kms, "value": w.vcv / (ms * 1e-3) / 1e9, "unit": UNIT,
                  "algorithmic_bytes": alg, "roofline_frac": alg / (kms * 1e-3) / 1e9 / peak,
                  "step_frac": alg / (ms * 1e-3) / 1e9 / peak, "steps": steps}
+        if w.vcv < 2e9:
+            gms = graph_replay_ms(share, agg, steps, stream, barrier)
+            if gms is not None:
+                entry["cuda_graph"] = {"ms_per_step": gms, "value": w.vcv / (gms * 1e-3) / 1e9, "unit": UNIT,
+                                       "step_frac": alg / (gms * 1e-3) / 1e9 / peak,
+                                       "note": "the same step replayed from a CUDA graph (no per-call host overhead)"}
         if w.joints:
             f, P, cv = share.dev_sets[0]
             vol = share.step(agg, 0)
@@ -394,6 +444,16 @@ def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_en
                 bytes_ = alg if store else alg - w.B * w.C * w.G ** 3 * 4
                 fused[label] = {"ms_per_step": fms, "value": w.vcv / (fms * 1e-3) / 1e9, "unit": UNIT,
                                 "algorithmic_bytes": bytes_, "step_frac": bytes_ / (fms * 1e-3) / 1e9 / peak}
+                gms = graph_replay_ms(share, agg, steps, stream, barrier,
+                                      body=lambda f, P, cv, out, store=store: agg.unprojection_soft_argmax(
+                                          f, P, cv, w.joints, w.method, store_volume=store))
+                if gms is not None:
+                    fused[label]["cuda_graph_ms_per_step"] = gms
+            gms = graph_replay_ms(share, agg, steps, stream, barrier,
+                                  body=lambda f, P, cv, out: agg.soft_argmax_3d(
+                                      agg.unprojection(f, P, cv, w.method, out=out, packed=agg.pack_features(f))[:, :w.joints], cv))
+            if gms is not None:
+                fused["two_kernel_cuda_graph_ms_per_step"] = gms
             f, P, cv = share.dev_sets[0]
             j = agg.unprojection_soft_argmax(f, P, cv, w.joints, w.method, store_volume=False)[1]
             fused["max_abs_diff_vs_two_kernel_mm"] = float((j - two).abs().max())

@@ -48,15 +48,23 @@ def _is_channels_last(features):
     return tuple(features.stride()) == (V * H * W * C, H * W * C, 1, W * C, C)
 
 
-def pack_features(features):
+def pack_features(features, out=None):
     """(B,V,C,H,W) -> the library's gather layout (opaque uint8 tensor).
     Lets a caller that reuses one set of feature maps for several grids pay the
-    layout pass once (`unprojection(..., packed=...)`)."""
+    layout pass once (`unprojection(..., packed=...)`).  `out`: a uint8 CUDA tensor of
+    `mvhmr_packed_bytes` bytes to pack into (a steady-state loop keeps one instead of
+    asking the allocator for hundreds of MB per step)."""
     dev = _lib.require_cuda(features)
     B, V, C, H, W = features.shape
     dt = _feat_dtype(features)
     L = _lib.load()
-    packed = torch.empty(L.mvhmr_packed_bytes(dt, B * V, C, H, W), dtype=torch.uint8, device=dev)
+    nbytes = L.mvhmr_packed_bytes(dt, B * V, C, H, W)
+    if out is None:
+        packed = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    else:
+        if out.dtype != torch.uint8 or out.device != dev or out.numel() != nbytes or not out.is_contiguous() or out.data_ptr() % 16:
+            raise ValueError("pack_features: `out` must be a contiguous, 16-byte aligned uint8 tensor of %d bytes on %s" % (nbytes, dev))
+        packed = out
     with torch.cuda.device(dev):
         _lib.check(L.mvhmr_pack_features(_lib.ptr(features.contiguous()), dt, _lib.ptr(packed),
                                          B * V, C, H, W, _lib.stream_ptr(dev)))

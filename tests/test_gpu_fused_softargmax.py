@@ -133,3 +133,18 @@ def test_fused_path_argument_errors():
         B, V, C, H, Wd, w.G, w.G, w.G, _lib.SOFTMAX, 0, _lib.ptr(ws), ws.numel(), _lib.ptr(ws), 16,
         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert rc == _lib.ERR_WORKSPACE
+
+
+def test_pack_features_into_a_caller_buffer():
+    w = syn.CONFIGS["cfg1"]
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    fresh = agg.pack_features(fd)
+    buf = torch.full_like(fresh, 0xAB)
+    assert agg.pack_features(fd, out=buf) is buf
+    assert torch.equal(buf, fresh)
+    assert torch.equal(agg.unprojection(fd, Pd, cvd, "softmax", packed=buf), agg.unprojection(fd, Pd, cvd, "softmax"))
+    with pytest.raises(ValueError):
+        agg.pack_features(fd, out=buf[:-16])
+    with pytest.raises(ValueError):
+        agg.pack_features(fd, out=buf.float())
