@@ -22,6 +22,8 @@
 //     texture latency.
 #include <cuda_fp16.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <vector>
 #include "mvhmr_common.cuh"
@@ -40,6 +42,10 @@ struct TexParams {
     int nq;                // channel quads = ceil(C / 4)
     int g0;                // first sample of tex[0] (absolute sample index)
     unsigned nzseg, nxb;   // z segments of 32 voxels; x blocks of 8 planes
+    unsigned nyb;          // y blocks
+    unsigned lane_axes;    // lane -> voxel mapping: 2 bits per lane bit (0 = z, 1 = x, 2 = y), lane bit 0 first.
+                           // The texture unit filters quads of 4 lanes: compact quads (2 z x 2 x) share texels
+    int zspan, xspan, yspan;   // voxels of one warp along each axis (product 32)
 };
 
 // blockDim = (32, 8): 8 rows of one (map, channel quad) plane per block, lanes along x
@@ -147,17 +153,28 @@ unproject_tex_kernel(const TexParams q)
 {
     const UnprojParams &p = q.u;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // block -> (sample, z segment, x block, y)
+    // block -> (sample, z segment, x block, y block); lane -> voxel inside the warp's zspan x xspan x yspan brick
     unsigned t = blockIdx.x;
-    const int vy = (int)(t % (unsigned)p.gy); t /= (unsigned)p.gy;
+    const unsigned yb = t % q.nyb; t /= q.nyb;
     const unsigned xb = t % q.nxb; t /= q.nxb;
     const int seg = (int)(t % q.nzseg);
     const int b = p.b0 + (int)(t / q.nzseg);
-    const int xi = (int)xb * (kTexThreads / 32) + warp;
-    if (xi >= p.nx) return;
-    const int vx = p.x_lo + xi, vz = seg * 32 + lane;
+    int dz = 0, dx = 0, dy = 0;
+    {
+        int sz = 0, sx = 0, sy = 0;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+            const unsigned ax = (q.lane_axes >> (2 * i)) & 3u, bit = (lane >> i) & 1u;
+            if (ax == 0) dz |= bit << sz++;
+            else if (ax == 1) dx |= bit << sx++;
+            else dy |= bit << sy++;
+        }
+    }
+    const int xi = ((int)xb * (kTexThreads / 32) + warp) * q.xspan + dx;
+    const int vy = (int)yb * q.yspan + dy, vz = seg * q.zspan + dz;
+    const int vx = p.x_lo + xi;
     const long long n = ((long long)vx * p.gy + vy) * p.gz + vz;
-    const bool mine = vz < p.gz && n >= p.n0 && n < p.n1;
+    const bool mine = xi < p.nx && vy < p.gy && vz < p.gz && n >= p.n0 && n < p.n1;
     if (!__any_sync(0xffffffffu, mine)) return;
 
     // ---- sampling positions of this voxel in every view (exact), as texture coordinates ----
@@ -357,8 +374,21 @@ extern "C" int mvhmr_unproject_aggregate_tex(const void *feats, int feat_dtype,
     p.rH = 1.0f / (float)H; p.rW = 1.0f / (float)W;
     q.nq = nq;
     q.samples_per_tex = (int)(kTexMaxRows / rows_per_sample);
-    q.nzseg = (unsigned)((gz + 31) / 32);
-    q.nxb = (unsigned)((p.nx + kTexThreads / 32 - 1) / (kTexThreads / 32));
+    {
+        // lane bits -> axes, lane bit 0 first ('z' / 'x' / 'y').  Default zxzzz: a warp covers 16 z of two
+        // x planes and every texture quad is 2 z x 2 x (MVHMR_TEX_LANES overrides: tuning knob)
+        const char *spec = getenv("MVHMR_TEX_LANES");
+        if (!spec || strlen(spec) != 5) spec = "zxzzz";
+        q.lane_axes = 0; q.zspan = q.xspan = q.yspan = 1;
+        for (int i = 0; i < 5; ++i) {
+            const unsigned ax = spec[i] == 'x' ? 1u : spec[i] == 'y' ? 2u : 0u;
+            q.lane_axes |= ax << (2 * i);
+            (ax == 0 ? q.zspan : ax == 1 ? q.xspan : q.yspan) *= 2;
+        }
+    }
+    q.nzseg = (unsigned)((gz + q.zspan - 1) / q.zspan);
+    q.nxb = (unsigned)((p.nx + q.xspan * (kTexThreads / 32) - 1) / (q.xspan * (kTexThreads / 32)));
+    q.nyb = (unsigned)((gy + q.yspan - 1) / q.yspan);
     const int per_launch = q.samples_per_tex * kTexMaxGroups;
     for (int g0 = b0; g0 < b1; g0 += per_launch) {
         const int g1 = g0 + per_launch < b1 ? g0 + per_launch : b1;
@@ -369,7 +399,7 @@ extern "C" int mvhmr_unproject_aggregate_tex(const void *feats, int feat_dtype,
             int rc = get_texture(planes + sample_bytes * s0, W, (int)(ns * rows_per_sample), pitch, &q.tex[k]);
             if (rc != MVHMR_OK) return rc;
         }
-        const long long blocks = (long long)p.nb * q.nzseg * q.nxb * gy;
+        const long long blocks = (long long)p.nb * q.nzseg * q.nxb * q.nyb;
         if (blocks > 0x7fffffffLL) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_tex: too many blocks in one call");
 #define MVHMR_TLAUNCH(VM, M, EX, FC) unproject_tex_kernel<VM, M, EX, FC><<<(unsigned)blocks, kTexThreads, 0, st>>>(q)
 #define MVHMR_TMETHOD(VM, EX, FC)                                        \
