@@ -424,6 +424,12 @@ def per_config_block(agg, dev, stream, barrier, peak, headline_name, headline_en
             sa_ms = e0.elapsed_time(e1) / steps
             entry["soft_argmax"] = {"joints": w.joints, "ms": sa_ms, "algorithmic_bytes": w.soft_argmax_bytes(),
                                     "roofline_frac": w.soft_argmax_bytes() / (sa_ms * 1e-3) / 1e9 / peak}
+            # the eager loop above is bound by the host (~50 us of Python per call): the same two launches from a graph
+            gms = graph_replay_ms(share, agg, steps, stream, barrier,
+                                  body=lambda f, P, cv, out: agg.soft_argmax_3d(out[:, :w.joints], cv))
+            if gms is not None:
+                entry["soft_argmax"]["cuda_graph_ms"] = gms
+                entry["soft_argmax"]["cuda_graph_roofline_frac"] = w.soft_argmax_bytes() / (gms * 1e-3) / 1e9 / peak
             # BASELINE.json's target path as ONE kernel: unproject + aggregate + soft-argmax
             # (mvhmr_unproject_aggregate_softargmax), with and without the volume store
             fused = {"two_kernel_step_ms": ms + sa_ms}

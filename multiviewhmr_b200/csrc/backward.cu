@@ -490,11 +490,15 @@ static void launch_bwd(int method, dim3 grid, size_t smem, cudaStream_t st, cons
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                   \
         kern<<<grid, kBwdWarps * 32, smem, st>>>(q);                                                          \
     }
-    switch (method) {
-    case MVHMR_SUM: MVHMR_BWD(MVHMR_SUM) break;
-    case MVHMR_MEAN: MVHMR_BWD(MVHMR_MEAN) break;
-    case MVHMR_MAX: MVHMR_BWD(MVHMR_MAX) break;
-    default: MVHMR_BWD(MVHMR_SOFTMAX) break;
+    if constexpr (ACC) {                 // the register accumulators serve sum / mean only: no max / softmax instantiation
+        if (method == MVHMR_SUM) MVHMR_BWD(MVHMR_SUM) else MVHMR_BWD(MVHMR_MEAN)
+    } else {
+        switch (method) {
+        case MVHMR_SUM: MVHMR_BWD(MVHMR_SUM) break;
+        case MVHMR_MEAN: MVHMR_BWD(MVHMR_MEAN) break;
+        case MVHMR_MAX: MVHMR_BWD(MVHMR_MAX) break;
+        default: MVHMR_BWD(MVHMR_SOFTMAX) break;
+        }
     }
 #undef MVHMR_BWD
 }

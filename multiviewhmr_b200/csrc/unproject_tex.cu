@@ -148,7 +148,7 @@ __device__ __forceinline__ f2 sample_position_fast(const float4 &P0, const float
 
 // EXACT: V == VMAX (no per-view guards); FULLC: C % 4 == 0 (no per-channel guards)
 template <int VMAX, int METHOD, bool EXACT, bool FULLC>
-__global__ void __launch_bounds__(kTexThreads, VMAX > 4 ? 4 : 1)   // V = 8: four CTAs per SM (64 registers) beat five with spills: 430 vs 467 us at cfg5's shape
+__global__ void __launch_bounds__(kTexThreads, VMAX > 4 ? 4 : 5)   // V <= 4: five CTAs per SM (44 registers); V = 8: four (64 registers) beat five with spills, 430 vs 467 us at cfg5's shape
 unproject_tex_kernel(const TexParams q)
 {
     const UnprojParams &p = q.u;
