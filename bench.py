@@ -593,6 +593,31 @@ def main():
     e2e_ms, e2e_reps, h2d, d2h = time_e2e(agg, share, e2e_steps, stream, barrier, dev, True, sampler)
     gpu_ms, gpu_reps, _, gpu_d2h = time_e2e(agg, share, e2e_steps, stream, barrier, dev, False, sampler)
 
+    # ---- optional collective, reported separately: every rank ends with the full volume ----
+    gather = None
+    if world > 1 and w.B % world == 0 and not args.no_extras:
+        per = w.B // world
+        full = torch.empty((w.B, w.C, w.G, w.G, w.G), dtype=torch.float32, device=dev)
+        full[rank * per:(rank + 1) * per].copy_(share.outs[0])
+        sharding.all_gather_volume(full, w.B, w.G, world)           # warm-up (NCCL channel setup)
+        barrier()
+        reps = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            sharding.all_gather_volume(full, w.B, w.G, world)
+            e1.record(stream)
+            barrier()
+            reps.append(e0.elapsed_time(e1))
+        tg = torch.tensor([sorted(reps)[1]], device=dev)
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        nbytes = full.numel() * 4
+        gather = {"ms": float(tg[0]), "bytes_total": nbytes, "busbw_gbs": nbytes * (world - 1) / world / (float(tg[0]) * 1e-3) / 1e9,
+                  "note": "sharding.all_gather_volume: ONE ncclAllGather straight into the full (B,C,G,G,G) volume over NVLink; "
+                          "NOT part of `value` — data-parallel consumers keep the volume sharded"}
+        del full
+        torch.cuda.empty_cache()
+
     if world > 1:
         t = torch.tensor([ms_per_step, e2e_ms, kernel_ms, gpu_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -636,6 +661,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "clocks": sampler.summary(),
         }
+        if gather is not None:
+            line["extras"] = {"all_gather_volume": gather}
         if world == 1 and not args.no_extras:
             head = {"workload": describe(w), "ms_per_step": ms_per_step, "kernel_ms": kernel_ms, "value": value, "unit": UNIT,
                     "algorithmic_bytes": alg, "roofline_frac": achieved / peak,

@@ -148,3 +148,22 @@ def test_pack_features_into_a_caller_buffer():
         agg.pack_features(fd, out=buf[:-16])
     with pytest.raises(ValueError):
         agg.pack_features(fd, out=buf.float())
+
+
+def test_fused_path_channels_last_maps_and_many_views():
+    """Channels-last maps gathered in place (no pack pass) and V = 12 (view blocks with carried fusion state)."""
+    w = workload(2, 4, 32, 40, 48, 24)
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    fcl = fd.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    assert agg._is_channels_last(fcl)
+    ref_vol, ref_j = agg.unprojection_soft_argmax(fd, Pd, cvd, 17, "softmax")
+    vol, joints = agg.unprojection_soft_argmax(fcl, Pd, cvd, 17, "softmax")
+    assert torch.equal(vol, ref_vol) and torch.equal(joints, ref_j)
+    w = workload(1, 12, 16, 32, 32, 20)
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    ref_vol = agg.unprojection(fd, Pd, cvd, "softmax")
+    vol, joints = agg.unprojection_soft_argmax(fd, Pd, cvd, 16, "softmax")
+    assert torch.equal(vol, ref_vol)
+    check_joints(joints, ref_vol, cv, 16)
