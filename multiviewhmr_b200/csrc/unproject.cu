@@ -264,6 +264,14 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     return pack_features_layout(feats, feat_dtype, packed, BV, C, H, W, packed_ps16(feat_dtype, C), stream);
 }
 
+static int sm_count()
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+}
+
 static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
                           const float *proj, const float *coord, const mvhmr_grid_t *grid_desc, float *out, unsigned out_flags,
                           int B, int V, int C, int H, int W,
@@ -336,6 +344,14 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         // whole 128-byte lines are worth more than equal ones (cfg5, gz = 80: 32+32+16 is 11 % faster
         // than 27+27+26).
         if (V > 4 && gz > lz_cap) lz = lz_cap;
+    }
+    if (tile_hint == 0 && !pool) {
+        // Small problems (cfg1: 64 CTA tasks for 148 SMs): shorter z segments while fewer than half of the SMs have a task.
+        // Results do not depend on the segmentation.
+        const long long yz_ = (long long)gy * gz;
+        const int nx_ = (int)((n1 - 1) / yz_) - (int)(n0 / yz_) + 1;
+        const long long rows = (long long)(b1 - b0) * gy * ((nx_ + kWarps - 1) / kWarps);
+        while (lz > 8 && 2 * rows * ((gz + lz - 1) / lz) <= sm_count()) lz = (lz + 1) / 2;
     }
     if (pool) {                                                     // pooled pairs (z, z+1) stay inside one segment
         if (lz_cap < 2) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate: pooled output: V=%d leaves no room for two voxels per task", V);
@@ -503,14 +519,6 @@ extern "C" int mvhmr_unproject_aggregate_fmt(const void *feats, int feat_dtype, 
     if (!coord && !grid) return fail(MVHMR_ERR_INVALID_ARGUMENT, "unproject_aggregate_fmt: give a coord volume or a grid descriptor");
     return unproject_impl(feats, feat_dtype, feat_layout, proj, coord, coord ? nullptr : grid, out, out_flags, B, V, C, H, W, gx, gy, gz, method,
                           b0, b1, n0, n1, n_origin, n_extent, tile_hint, ws, ws_bytes, stream);
-}
-
-static int sm_count()
-{
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    return sms;
 }
 
 extern "C" size_t mvhmr_unproject_softargmax_workspace_bytes(int B, int J)
