@@ -191,7 +191,10 @@ int mvhmr_unproject_aggregate_fmt(const void *feats, int feat_dtype, int feat_la
 /* Reduced-precision fast path for callers inside BASELINE.json's bf16 tolerance (1e-2 relative):
  * the bilinear samples are taken by the texture units from fp16 copies of the maps (hardware
  * interpolation weights are 1.8 fixed point).  Measured deviation from the reference on N(0,1)
- * maps: about 4e-3 relative — never use it where the fp32 contract (1e-5) applies.
+ * maps: about 4e-3 relative — never use it where the fp32 contract (1e-5) applies.  The error
+ * is ABSOLUTE in nature (about |texel| / 256 per corner): a volume that only grazes the edge of the maps
+ * (a fraction of a percent of non-zero voxels with values of a few hundredths) can show several
+ * percent relative deviation at the same 3e-3 absolute error.
  *   feats  (B,V,C,H,W) NCHW, fp32 or bf16 (|x| > 65504 saturates in fp16)
  *   exactly one of coord / grid non-NULL; out (B,C,n_extent) fp32 as in mvhmr_unproject_aggregate
  *   V <= 8 and V*ceil(C/4)*(H+1) <= 8192, else MVHMR_ERR_INVALID_ARGUMENT (use the exact path)
