@@ -22,6 +22,18 @@ namespace mvhmr {
 #ifndef MVHMR_LZCAP
 #define MVHMR_LZCAP 32
 #endif
+// texel gather: read-only path; MVHMR_LDG_EVICT_LAST (tuning build) asks L1 to keep the footprint
+__device__ __forceinline__ uint4 ldg_texel(const char *p)
+{
+#ifdef MVHMR_LDG_EVICT_LAST
+    uint4 r;
+    asm volatile("ld.global.nc.L1::evict_last.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+#else
+    return __ldg(reinterpret_cast<const uint4 *>(p));
+#endif
+}
+
 constexpr int kWarps = MVHMR_WARPS;       // warps per CTA: consecutive x planes share their texel footprint in L1
 constexpr unsigned kNotMine = 0xffffffffu;   // view-0 offset of a voxel outside the shard window (real offsets are multiples of 16)
 constexpr int kLzMax = 32;                // voxels of one warp task (z segment): one per lane in phase A
@@ -189,10 +201,10 @@ unproject_kernel(const UnprojParams p)
                         const unsigned t = o + (unsigned)(v0 + v) * p.plane32;
                         const char *q0 = lane_base + t;
                         const char *q1 = lane_base + (t + row);
-                        tex[v][0] = __ldg(reinterpret_cast<const uint4 *>(q0));
-                        tex[v][1] = __ldg(reinterpret_cast<const uint4 *>(q0 + px));
-                        tex[v][2] = __ldg(reinterpret_cast<const uint4 *>(q1));
-                        tex[v][3] = __ldg(reinterpret_cast<const uint4 *>(q1 + px));
+                        tex[v][0] = ldg_texel(q0);
+                        tex[v][1] = ldg_texel(q0 + px);
+                        tex[v][2] = ldg_texel(q1);
+                        tex[v][3] = ldg_texel(q1 + px);
                         cur[v] = o;
                     }
                 }
