@@ -70,7 +70,7 @@ summary('prof_r2_tex_v1_cfg3.ncu-rep',
 launch_shares('r2b_bench_launches.csv', 'r2_bench_launches.csv', 'r2_bench_launch_shares.txt',
               'ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline\n'
               '(cold-cache, serialised launches: shares, not absolutes; the first 600 launches cover the headline loop, both e2e legs and the start of the per-config block)\n')
-for src, dst in (('r2b_bench_final.json', 'r2_bench_line.json'), ('r2b_bench_n2.json', 'r2_bench_line_n2.json'), ('r2b_bench_n8.json', 'r2_bench_line_n8.json')):
+for src, dst in (('r2b_bench_final.json', 'r2_bench_line.json'), ('r2b_bench_n2.json', 'r2_bench_line_n2.json'), ('r2b_bench_n4.json', 'r2_bench_line_n4.json'), ('r2b_bench_n8.json', 'r2_bench_line_n8.json')):
     p = os.path.join(GO, src)
     if os.path.exists(p):
         open(os.path.join(PR, dst), 'w').write(open(p).read().strip().splitlines()[-1] + '\n')
