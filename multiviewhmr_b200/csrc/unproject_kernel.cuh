@@ -80,14 +80,16 @@ unproject_kernel(const UnprojParams p)
     // over every voxel its warp produces for the current sample; it is flushed when the warp moves on
     // to another sample (tasks are dealt sample-major, so at most once per sample) and at the end.
     float4 *sa_xyz = reinterpret_cast<float4 *>(recs + p.off_xyz);   // [32] coordinates of the task's voxels
-    float sa_m = -FLT_MAX, sa_S = 0.0f, sa_X = 0.0f, sa_Y = 0.0f, sa_Z = 0.0f;
+    float sa_m = -FLT_MAX;
+    u64 sa_SX = pk(0.0f, 0.0f), sa_YZ = pk(0.0f, 0.0f);          // (sum e, sum e*x), (sum e*y, sum e*z)
     int sa_b = -1;
     auto sa_flush = [&]() {
         if (sa_b >= 0 && lane < p.sa_J) {
             float *o = p.sa_rec + (((size_t)sa_b * p.sa_J + lane) * ((size_t)gridDim.x * kWarps) + (size_t)blockIdx.x * kWarps + warp) * 5;
-            o[0] = sa_m; o[1] = sa_S; o[2] = sa_X; o[3] = sa_Y; o[4] = sa_Z;
+            const f2 sx = upk(sa_SX), yz = upk(sa_YZ);
+            o[0] = sa_m; o[1] = sx.x; o[2] = sx.y; o[3] = yz.x; o[4] = yz.y;
         }
-        sa_m = -FLT_MAX; sa_S = sa_X = sa_Y = sa_Z = 0.0f;
+        sa_m = -FLT_MAX; sa_SX = sa_YZ = pk(0.0f, 0.0f);
     };
 
     // Persistent CTAs.  A CTA task = kWarps consecutive x planes of one (sample, z segment, y)
@@ -146,7 +148,7 @@ unproject_kernel(const UnprojParams p)
             Y = __fadd_rn(rot_row(__ldg(R + 3), __ldg(R + 4), __ldg(R + 5), d0, d1, d2), c1);
             Z = __fadd_rn(rot_row(__ldg(R + 6), __ldg(R + 7), __ldg(R + 8), d0, d1, d2), c2);
         }
-        if (OUT == 3) sa_xyz[lane] = make_float4(X, Y, Z, 0.0f);
+        if (OUT == 3) sa_xyz[lane] = make_float4(1.0f, X, Y, Z);   // (1, x, y, z): the sums (S, X) and (Y, Z) advance as two packed FMAs
         // lane / steps by multiplication (exact for lane < 32, steps <= 32)
         const unsigned g_of_lane = ((unsigned)lane * (zn == p.lz ? p.magic_full : p.magic_last)) >> 16;
         unsigned char *rec = recs + lane * rec_bytes + g_of_lane * 16;
@@ -323,16 +325,15 @@ unproject_kernel(const UnprojParams p)
             }
             const float mn = fmaxf(sa_m, mt);
             const float r = ex2_approx((sa_m - mn) * kLog2e);        // 1 if the max stands, 0 for the first task
-            sa_S *= r; sa_X *= r; sa_Y *= r; sa_Z *= r;
+            sa_SX = mul2(sa_SX, pk(r, r)); sa_YZ = mul2(sa_YZ, pk(r, r));
             sa_m = mn;
             const float nm = -mn * kLog2e;
             auto absorb_voxel = [&](float h, int z) {
-                const float4 xyz = sa_xyz[z];
+                const float4 c1 = sa_xyz[z];                         // (1, x, y, z)
                 const float e = ex2_approx(__fmaf_rn(h, kLog2e, nm));
-                sa_S += e;
-                sa_X = __fmaf_rn(e, xyz.x, sa_X);
-                sa_Y = __fmaf_rn(e, xyz.y, sa_Y);
-                sa_Z = __fmaf_rn(e, xyz.z, sa_Z);
+                const u64 ee = pk(e, e);
+                sa_SX = fma2(ee, pk(c1.x, c1.y), sa_SX);
+                sa_YZ = fma2(ee, pk(c1.z, c1.w), sa_YZ);
             };
             if (LPB != 0 && zn == kLzMax) {
 #pragma unroll
