@@ -146,6 +146,17 @@ __device__ __forceinline__ f2 sample_position_fast(const float4 &P0, const float
     return i;
 }
 
+// A / S with the reciprocal on the FMA pipe: the XU (MUFU) is this kernel's busiest pipe (157 -> 154 us at cfg3).  S is in [1, V]: magic-constant seed (12 % off), two Newton steps -> 2e-4 relative, far inside the path's budget.
+__device__ __forceinline__ f2 softmax_result_fma(u64 A, u64 S)
+{
+    const f2 s = upk(S);
+    u64 r = pk(__int_as_float(0x7EF311C3 - __float_as_int(s.x)), __int_as_float(0x7EF311C3 - __float_as_int(s.y)));
+    const u64 two = pk(2.0f, 2.0f), ns = pk(-s.x, -s.y);
+    r = mul2(r, fma2(ns, r, two));
+    r = mul2(r, fma2(ns, r, two));
+    return upk(mul2(A, r));
+}
+
 // EXACT: V == VMAX (no per-view guards); FULLC: C % 4 == 0 (no per-channel guards)
 template <int VMAX, int METHOD, bool EXACT, bool FULLC>
 __global__ void __launch_bounds__(kTexThreads, VMAX > 4 ? 4 : 5)   // V <= 4: five CTAs per SM (44 registers); V = 8: four (64 registers) beat five with spills, 430 vs 467 us at cfg5's shape
@@ -237,7 +248,9 @@ unproject_tex_kernel(const TexParams q)
         Fuse2<METHOD, VMAX, EXACT> f0, f1;
         f0.absorb(&s[0][0], 2, p.V, true);
         f1.absorb(&s[0][1], 2, p.V, true);
-        f2 r0 = f0.result(Vf), r1 = f1.result(Vf);
+        f2 r0, r1;
+        if (METHOD == MVHMR_SOFTMAX) { r0 = softmax_result_fma(f0.a, f0.S); r1 = softmax_result_fma(f1.a, f1.S); }
+        else { r0 = f0.result(Vf); r1 = f1.result(Vf); }
         if (anynan && nanpos) { r0.x = r0.y = r1.x = r1.y = __int_as_float(0x7fc00000); }   // NaN propagates through every fusion mode
         if (mine) {
             __stcs(o, r0.x);
