@@ -458,9 +458,23 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned resident = (unsigned)sms * MVHMR_MINBLOCKS;       // one CTA (or MINBLOCKS) per SM, persistent
-    p.ychunk = 1;                                                    // largest y sweep that still leaves >= 6 rounds
-    for (unsigned yc = (V > 4 ? 2 : 8); yc > 1; yc >>= 1)            // the uncached path prefers short sweeps
-        if ((unsigned)p.ty % yc == 0 && ntasks / yc >= 6ll * resident) { p.ychunk = yc; break; }
+    // Consecutive tasks (y rows) a CTA takes per chunk.  The chunks are dealt round-robin, so a CTA ends up with
+    // ceil(chunks / CTAs) * ychunk tasks: the candidate that minimises this tail wins (cfg5 at 8 samples per GPU:
+    // 65 tasks per CTA with chunks of 5 against 66 with chunks of 2 — 1081 vs 1095 us), ties go to the
+    // earlier candidate.  The cached path (V <= 4) likes longer sweeps (texel rows stay in L1), the uncached one
+    // shorter ones (measured: scripts/ychunk_sweep.py).
+    {
+        static const unsigned cand_cached[] = {4, 7, 8, 2, 1}, cand_uncached[] = {5, 3, 2, 1};
+        const unsigned *cand = V > 4 ? cand_uncached : cand_cached;
+        const int ncand = V > 4 ? 4 : 5;
+        long long best = -1;
+        p.ychunk = 1;
+        for (int i = 0; i < ncand; ++i) {
+            const long long chunks = (ntasks + cand[i] - 1) / cand[i];
+            const long long per_cta = (chunks + resident - 1) / resident * cand[i];
+            if (best < 0 || per_cta < best) { best = per_cta; p.ychunk = cand[i]; }
+        }
+    }
     if (const char *env = getenv("MVHMR_YCHUNK")) { const int v = atoi(env); if (v >= 1) p.ychunk = (unsigned)v; }   // tuning knob
     const unsigned nchunk = (unsigned)((ntasks + p.ychunk - 1) / p.ychunk);
     const dim3 grid(nchunk < resident ? nchunk : resident);

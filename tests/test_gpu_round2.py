@@ -395,3 +395,19 @@ def test_fast_path_rejects_what_it_cannot_do():
     fr = f[:, :4].clone().requires_grad_(True)
     with pytest.raises(ValueError):
         agg.unprojection(fr, P[:, :4], cv, "sum", precision="fast")
+
+
+@pytest.mark.parametrize("V", [4, 8])
+def test_task_chunking_does_not_change_results(monkeypatch, V):
+    """The persistent CTAs take their tasks in chunks of `ychunk` consecutive y rows (chosen per launch from the
+    tail it leaves; MVHMR_YCHUNK overrides): any chunking, also one that does not divide the row count, gives
+    the same bits."""
+    w = syn.Workload("t", B=3, V=V, C=32, H=40, W=40, G=36)
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    monkeypatch.delenv("MVHMR_YCHUNK", raising=False)
+    ref = agg.unprojection(fd, Pd, cvd, "softmax")
+    assert rel_l2(ref.cpu().numpy(), oracle.unprojection(f, P, cv, "softmax")) < OUR_TOL_SOFTMAX
+    for yc in ("1", "3", "5", "7", "16", "1000"):
+        monkeypatch.setenv("MVHMR_YCHUNK", yc)
+        assert torch.equal(agg.unprojection(fd, Pd, cvd, "softmax"), ref), yc
