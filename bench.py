@@ -22,8 +22,13 @@ Rank 0 prints ONE JSON line.
              inside the timed region (three streams, double-buffered).  `e2e.consumer_on_gpu`
              is the variant whose consumer stays on the GPU (soft-argmax -> (B,C,3) to host).
   configs    (N=1 only) every BASELINE config cfg1..cfg5 device-resident: ms, Gvcv/s and the
-             fraction of the HBM roofline of the fused kernel (cfg3 also its soft-argmax)
+             fraction of the HBM roofline of the fused kernel; the small configs also replayed from
+             CUDA graphs (`cuda_graph`); cfg3 also its soft-argmax, the ONE-kernel fused
+             unproject+aggregate+soft-argmax path (`fused_soft_argmax`: volume stored / joints only)
+             and the reduced-precision texture path (`fast_path`)
   extras.backward (N=1 only) the gradient kernels at cfg2 and cfg4 with their roofline
+  extras.all_gather_volume (N>1 only) the optional NCCL all-gather of the sharded volume, timed
+             separately — it is not part of `value`
 
 `--impl reference` times the reference's own CPU path (oracle/torch_port.py: the same
 ATen calls in the same order, all host threads) on a bounded sample of the same
