@@ -331,11 +331,17 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     const int nch_pass = nchunks < kVecPass ? nchunks : kVecPass;
     const int nvec = bf ? 2 * nch_pass : nch_pass;
     const int VP = (V <= 4) ? 4 : ((V + 7) & ~7);
-    int lz_cap = 256 / nvec;                                       // output tile <= 4 KB per warp
-    if (lz_cap < 4) lz_cap = 4;
-    if (lz_cap > MVHMR_LZCAP) lz_cap = MVHMR_LZCAP;
     const int rec_bytes = V * 16 + VP * 4;
-    while (lz_cap > 1 && (size_t)lz_cap * rec_bytes > 12 * 1024) lz_cap >>= 1;             // voxel records <= 12 KB per warp
+    // Longest z segment whose records + output tile fit the shared-memory budget of a warp (what is left of the
+    // 256 KB is the L1 that holds the texel footprint), in whole 32-byte sectors of the output rows: cfg4
+    // (C = 64, V = 8) takes 24 voxels — 2.00 ms against 2.12 ms with 16 and 2.25 ms with 20 (scripts/lz_sweep.py).
+    size_t smem_cap = 160 * 1024;
+    if (const char *env = getenv("MVHMR_SMEM_CAP_KB")) { const int v = atoi(env); if (v >= 16 && v <= 220) smem_cap = (size_t)v * 1024; }   // tuning knob
+    const long long per_warp = (long long)(smem_cap / kWarps) - (32 / nch_pass) * 16 - 15 - (sa ? kLzMax * 16 : 0);
+    int lz_cap = per_warp > 0 ? (int)(per_warp / (rec_bytes + nvec * 16)) : 1;
+    if (lz_cap > MVHMR_LZCAP) lz_cap = MVHMR_LZCAP;
+    if (lz_cap >= 8) lz_cap &= ~7;
+    if (lz_cap < 1) lz_cap = 1;
     int lz = (int)tile_hint;
     if (lz == 0) {
         const int parts = (gz + lz_cap - 1) / lz_cap;               // smallest equal split of a z row
@@ -343,7 +349,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         // The uncached path (V > 4) has no z-run state to amortise: full segments whose stores are
         // whole 128-byte lines are worth more than equal ones (cfg5, gz = 80: 32+32+16 is 11 % faster
         // than 27+27+26).
-        if (V > 4 && gz > lz_cap) lz = lz_cap;
+        if ((V > 4 || lz_cap < kLzMax) && gz > lz_cap) lz = lz_cap;
     }
     if (tile_hint == 0 && !pool) {
         // Small problems (cfg1: 64 CTA tasks for 148 SMs): shorter z segments while fewer than half of the SMs have a task.
@@ -364,7 +370,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         off_tile = (lz * rec_bytes + (32 / nch_pass) * 16 + 15) & ~15;   // + per-group skew
         warp_smem = off_tile + lz * nvec * 16 + (sa ? kLzMax * 16 : 0);  // + the task's voxel coordinates
         smem = (size_t)warp_smem * kWarps;
-        if (smem <= 160 * 1024 || lz == 1 || (pool && lz == 2)) break;
+        if (smem <= smem_cap || lz == 1 || (pool && lz == 2)) break;
         lz = (lz + 1) / 2;
         if (pool) lz = (lz + 1) & ~1;
     }

@@ -1,0 +1,32 @@
+"""MVHMR_LZ sweep (voxels per warp task): fused kernel over pre-packed planes, min of 6.
+usage: python scripts/lz_sweep.py cfg4:16,cfg5:8 8,16,24,32"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from multiviewhmr_b200 import synthetic as syn, aggregation as agg
+dev = torch.device('cuda:0')
+for case in sys.argv[1].split(','):
+    name, B = case.split(':')
+    w = syn.CONFIGS[name]
+    w = syn.Workload(w.name, int(B), w.V, w.C, w.H, w.W, w.G, w.method, w.dtype, w.joints, w.cuboid_side)
+    f, P, cv, c = syn.make_inputs(w)
+    fd, Pd, cvd = f.to(dev), P.to(dev), cv.to(dev)
+    if w.dtype == 'bf16':
+        fd = fd.bfloat16()
+    out = torch.empty((w.B, w.C, w.G, w.G, w.G), device=dev)
+    packed = agg.pack_features(fd)
+    line = []
+    for lz in ['auto'] + sys.argv[2].split(','):
+        if lz == 'auto':
+            os.environ.pop('MVHMR_LZ', None)
+        else:
+            os.environ['MVHMR_LZ'] = lz
+        fn = lambda: agg.unprojection(fd, Pd, cvd, w.method, out=out, packed=packed)
+        for _ in range(2): fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(6):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+        line.append('%s=%.1f' % (lz, min(ts) * 1e3))
+    print(case, ' '.join(line), flush=True)
