@@ -344,12 +344,12 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     if (lz_cap < 1) lz_cap = 1;
     int lz = (int)tile_hint;
     if (lz == 0) {
-        const int parts = (gz + lz_cap - 1) / lz_cap;               // smallest equal split of a z row
-        lz = (gz + parts - 1) / parts;
-        // The uncached path (V > 4) has no z-run state to amortise: full segments whose stores are
-        // whole 128-byte lines are worth more than equal ones (cfg5, gz = 80: 32+32+16 is 11 % faster
-        // than 27+27+26).
-        if ((V > 4 || lz_cap < kLzMax) && gz > lz_cap) lz = lz_cap;
+        // fewest segments, split evenly, then rounded up to whole 32-byte sectors of the output rows: segments
+        // that end inside a sector cost a read-modify-write per row (gz = 80: 32+32+16 is 9-11 % faster than
+        // 27+27+26 on both the cached and the uncached path; C = 64: 24+24+16 against 20+20+20+4)
+        const int parts = (gz + lz_cap - 1) / lz_cap;
+        lz = ((gz + parts - 1) / parts + 7) & ~7;
+        if (lz > lz_cap) lz = lz_cap;
     }
     if (tile_hint == 0 && !pool) {
         // Small problems (cfg1: 64 CTA tasks for 148 SMs): shorter z segments while fewer than half of the SMs have a task.
