@@ -7,6 +7,7 @@
 // the features, but they still take part in the fusion.  One thread per voxel recomputes the
 // cells with the forward's exact arithmetic, re-samples the NCHW maps and scatters with
 // red.global.add.f32 into an fp32 gradient buffer (zeroed by the caller).
+#include <cstdlib>
 #include "mvhmr_common.cuh"
 #include "unproject_device.cuh"
 
@@ -563,6 +564,7 @@ extern "C" int mvhmr_unproject_aggregate_backward_ws(const float *grad_out, cons
         int lz = 256 / nvec;                                           // gradient tile <= 4 KB per warp
         if (lz < 4) lz = 4;
         if (lz > 32) lz = 32;
+        if (const char *env = getenv("MVHMR_BWD_LZ")) { const int v = atoi(env); if (v >= 1 && v <= 32) lz = v; }   // tuning knob
         const int VP = (V + 3) & ~3;
         q.rec_bytes = V * 16 + VP * 4;
         while (lz > 1 && (size_t)lz * q.rec_bytes > 12 * 1024) lz >>= 1;   // voxel records <= 12 KB per warp
