@@ -477,6 +477,9 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         p.ychunk = 1;
         for (int i = 0; i < ncand; ++i) {
             const long long chunks = (ntasks + cand[i] - 1) / cand[i];
+            // long sweeps only when they still leave a few rounds: with one or two rounds the CTAs spread over all
+            // samples at once and their maps fall out of L2 (pooled cfg2, 1024 tasks: 280 us in chunks of 7, 259 us in 1)
+            if (cand[i] > 1 && chunks < 4ll * resident) continue;
             const long long per_cta = (chunks + resident - 1) / resident * cand[i];
             if (best < 0 || per_cta < best) { best = per_cta; p.ychunk = cand[i]; }
         }
