@@ -338,7 +338,8 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     size_t smem_cap = 160 * 1024;
     if (const char *env = getenv("MVHMR_SMEM_CAP_KB")) { const int v = atoi(env); if (v >= 16 && v <= 220) smem_cap = (size_t)v * 1024; }   // tuning knob
     const long long per_warp = (long long)(smem_cap / kWarps) - (32 / nch_pass) * 16 - 15 - (sa ? kLzMax * 16 : 0);
-    int lz_cap = per_warp > 0 ? (int)(per_warp / (rec_bytes + nvec * 16)) : 1;
+    const int tile_row = ndhwc ? 0 : nvec * 16;                     // channels-last-3D output leaves from registers: no tile
+    int lz_cap = per_warp > 0 ? (int)(per_warp / (rec_bytes + tile_row)) : 1;
     if (lz_cap > MVHMR_LZCAP) lz_cap = MVHMR_LZCAP;
     if (lz_cap >= 8) lz_cap &= ~7;
     if (lz_cap < 1) lz_cap = 1;
@@ -368,7 +369,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     size_t smem;
     for (;;) {                                                      // a hint that does not fit is shortened
         off_tile = (lz * rec_bytes + (32 / nch_pass) * 16 + 15) & ~15;   // + per-group skew
-        warp_smem = off_tile + lz * nvec * 16 + (sa ? kLzMax * 16 : 0);  // + the task's voxel coordinates
+        warp_smem = off_tile + lz * tile_row + (sa ? kLzMax * 16 : 0);   // + the task's voxel coordinates
         smem = (size_t)warp_smem * kWarps;
         if (smem <= smem_cap || lz == 1 || (pool && lz == 2)) break;
         lz = (lz + 1) / 2;
@@ -450,7 +451,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         p.magic_last = (65536u + steps_last - 1) / steps_last;
     }
     p.warp_smem = warp_smem; p.rec_bytes = rec_bytes; p.off_tile = off_tile;
-    p.off_xyz = off_tile + lz * nvec * 16;
+    p.off_xyz = off_tile + lz * tile_row;
     p.sa_J = sa_J; p.sa_rec = sa_rec;
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
