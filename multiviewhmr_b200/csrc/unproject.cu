@@ -28,6 +28,7 @@
 //     is written exactly once and no per-view volume exists anywhere.
 #include <cuda_bf16.h>
 #include <cstdlib>
+#include <atomic>
 #include "mvhmr_common.cuh"
 #include "unproject_device.cuh"
 
@@ -264,6 +265,27 @@ extern "C" int mvhmr_pack_features(const void *feats, int feat_dtype, void *pack
     return pack_features_layout(feats, feat_dtype, packed, BV, C, H, W, packed_ps16(feat_dtype, C), stream);
 }
 
+// Chunk counters of the launches in flight: a ring of slots, one per launch, zeroed on the launch's stream right
+// before the kernel.  (The library still owns no caller-visible state: a slot is scratch for the duration of one
+// launch; 1024 launches would have to be in flight at once for two to share one.)
+__device__ unsigned g_deal_ring[1024];
+static std::atomic<unsigned> g_deal_ticket{0};
+
+static unsigned *deal_slot(cudaStream_t st)
+{
+    static unsigned *base[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    if (!base[dev]) {
+        void *ptr = nullptr;
+        if (cudaGetSymbolAddress(&ptr, g_deal_ring) != cudaSuccess) return nullptr;
+        base[dev] = (unsigned *)ptr;
+    }
+    unsigned *slot = base[dev] + (g_deal_ticket.fetch_add(1u) & 1023u);
+    if (cudaMemsetAsync(slot, 0, sizeof(unsigned), st) != cudaSuccess) return nullptr;
+    return slot;
+}
+
 static int sm_count()
 {
     int dev = 0, sms = 148;
@@ -338,8 +360,14 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     size_t smem_cap = 160 * 1024;
     if (const char *env = getenv("MVHMR_SMEM_CAP_KB")) { const int v = atoi(env); if (v >= 16 && v <= 220) smem_cap = (size_t)v * 1024; }   // tuning knob
     const long long per_warp = (long long)(smem_cap / kWarps) - (32 / nch_pass) * 16 - 15 - (sa ? kLzMax * 16 : 0);
-    const int tile_row = ndhwc ? 0 : nvec * 16;                     // channels-last-3D output leaves from registers: no tile
-    int lz_cap = per_warp > 0 ? (int)(per_warp / (rec_bytes + tile_row)) : 1;
+    // Per voxel of a segment: formats 0 / 3 write the output tile over the dead voxel records (pitch = the longer of
+    // the two), the pooled format keeps records + tile, channels-last-3D output leaves from registers (no tile).
+    // one channel pass (the records die with the step), and only the VMAX = 8 instantiations (launch_unproject_gather)
+    const bool alias = !ndhwc && !pool && nchunks <= kVecPass && (V == 8 || (!bf && V > 4));
+    const int rec_pitch = alias ? ((rec_bytes > nvec * 16 ? rec_bytes : nvec * 16) | 16) : rec_bytes;   // an odd number of 16-byte units (see the kernel)
+    const int tile_row = alias || ndhwc ? 0 : nvec * 16;
+    const int dummy_bytes = alias ? (rec_bytes + 15) & ~15 : 0;
+    int lz_cap = per_warp - dummy_bytes > 0 ? (int)((per_warp - dummy_bytes) / (rec_pitch + tile_row)) : 1;
     if (lz_cap > MVHMR_LZCAP) lz_cap = MVHMR_LZCAP;
     if (lz_cap >= 8) lz_cap &= ~7;
     if (lz_cap < 1) lz_cap = 1;
@@ -368,8 +396,9 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     int off_tile, warp_smem;
     size_t smem;
     for (;;) {                                                      // a hint that does not fit is shortened
-        off_tile = (lz * rec_bytes + (32 / nch_pass) * 16 + 15) & ~15;   // + per-group skew
-        warp_smem = off_tile + lz * tile_row + (sa ? kLzMax * 16 : 0);   // + the task's voxel coordinates
+        off_tile = (lz * rec_pitch + (32 / nch_pass) * 16 + 15) & ~15;  // + per-group skew
+        warp_smem = off_tile + lz * tile_row + dummy_bytes + (sa ? kLzMax * 16 : 0);   // (+ dummy record) (+ the task's voxel coordinates)
+        if (const char *env = getenv("MVHMR_SMEM_PAD")) warp_smem += atoi(env) & ~15;   // experiment: unused bytes per warp
         smem = (size_t)warp_smem * kWarps;
         if (smem <= smem_cap || lz == 1 || (pool && lz == 2)) break;
         lz = (lz + 1) / 2;
@@ -451,7 +480,9 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         p.magic_last = (65536u + steps_last - 1) / steps_last;
     }
     p.warp_smem = warp_smem; p.rec_bytes = rec_bytes; p.off_tile = off_tile;
-    p.off_xyz = off_tile + lz * tile_row;
+    p.alias = alias;
+    p.off_dummy = off_tile + lz * tile_row;
+    p.off_xyz = p.off_dummy + dummy_bytes;
     p.sa_J = sa_J; p.sa_rec = sa_rec;
     p.Hf = (float)H; p.Wf = (float)W;
     p.sx = (float)(W - 1) / 2.0f; p.sy = (float)(H - 1) / 2.0f;
@@ -465,12 +496,23 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned resident = (unsigned)sms * MVHMR_MINBLOCKS;       // one CTA (or MINBLOCKS) per SM, persistent
-    // Consecutive tasks (y rows) a CTA takes per chunk.  The chunks are dealt round-robin, so a CTA ends up with
-    // ceil(chunks / CTAs) * ychunk tasks: the candidate that minimises this tail wins (cfg5 at 8 samples per GPU:
-    // 65 tasks per CTA with chunks of 5 against 66 with chunks of 2 — 1081 vs 1095 us), ties go to the
-    // earlier candidate.  The cached path (V <= 4) likes longer sweeps (texel rows stay in L1), the uncached one
-    // shorter ones (measured: scripts/ychunk_sweep.py).
-    {
+    // How the CTA chunks (runs of consecutive y rows) are dealt.
+    //  * Eight-view kernels, dynamically (a global counter, unproject_kernel.cuh): once the output tile lives in the
+    //    records their L1 holds the footprint and they wait on L2 instead — and the SMs do not all see the same L2
+    //    latency: +-10 % spread of the per-SM time, which a static deal turns into the slowest SM's time (cfg5 at
+    //    32 samples: 4.55 ms static, 3.85 ms dynamic, 4.16 ms before either change).  Sweeps of eight rows keep the
+    //    CTA-wide hand-over rare; small problems get shorter chunks until every CTA sees at least eight.
+    //  * Four-view (cached, software-pipelined) kernels, statically: their warps must never meet — the hand-over
+    //    barrier costs them 5-7 % (cfg2 293 -> 309 us) — and their per-SM times are even.  A CTA ends up with
+    //    ceil(chunks / CTAs) * ychunk tasks: the candidate that minimises this tail wins, ties go to the earlier
+    //    candidate (longer sweeps keep texel rows in L1), long sweeps only when they leave a few rounds
+    //    (scripts/ychunk_sweep.py).  The fused soft-argmax format is dealt statically too: its records would
+    //    otherwise be summed in a different order from run to run.
+    const bool dynamic_deal = V > 4 && !sa && !getenv("MVHMR_STATIC_DEAL");
+    if (dynamic_deal) {
+        p.ychunk = 8;
+        while (p.ychunk > 1 && ntasks / p.ychunk < 8ll * resident) p.ychunk >>= 1;
+    } else {
         static const unsigned cand_cached[] = {4, 7, 8, 2, 1}, cand_uncached[] = {5, 3, 2, 1};
         const unsigned *cand = V > 4 ? cand_uncached : cand_cached;
         const int ncand = V > 4 ? 4 : 5;
@@ -478,8 +520,6 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         p.ychunk = 1;
         for (int i = 0; i < ncand; ++i) {
             const long long chunks = (ntasks + cand[i] - 1) / cand[i];
-            // long sweeps only when they still leave a few rounds: with one or two rounds the CTAs spread over all
-            // samples at once and their maps fall out of L2 (pooled cfg2, 1024 tasks: 280 us in chunks of 7, 259 us in 1)
             if (cand[i] > 1 && chunks < 4ll * resident) continue;
             const long long per_cta = (chunks + resident - 1) / resident * cand[i];
             if (best < 0 || per_cta < best) { best = per_cta; p.ychunk = cand[i]; }
@@ -488,6 +528,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     if (const char *env = getenv("MVHMR_YCHUNK")) { const int v = atoi(env); if (v >= 1) p.ychunk = (unsigned)v; }   // tuning knob
     const unsigned nchunk = (unsigned)((ntasks + p.ychunk - 1) / p.ychunk);
     const dim3 grid(nchunk < resident ? nchunk : resident);
+    p.deal = dynamic_deal ? deal_slot(st) : nullptr;                 // NULL: static round-robin (also when no slot could be had)
     const unsigned g = grid.x;
     if (sa) {
         // one record per (sample, joint, CTA, warp); slots a warp never reaches stay zero (= empty for the merge)

@@ -75,6 +75,24 @@ unproject_kernel(const UnprojParams p)
     const unsigned px = lpb > 0 ? 1u << lpb : (unsigned)p.pstride, row = (unsigned)p.Wp * px;
     const int wbytes = EXACT ? VMAX * 16 : p.V * 16;
     const int rec_bytes = EXACT ? VMAX * 16 + ((VMAX + 3) & ~3) * 4 : p.rec_bytes;
+    // Formats 0 and 3 keep NO separate output tile: row z of the tile is written over the record of voxel z, which
+    // is dead by then (its weights and offsets were read earlier in the same step, in program order; lane groups
+    // only ever touch the slots of their own run).  The records' pitch is stretched to a tile row where that is
+    // longer.  The shared memory this saves (64 KB per CTA at C = 32) is L1 for the texel footprint: with eight
+    // views that is worth ~10 %.  Steps beyond the end of a run read a dummy record of zeros
+    // instead of record 0, which may already be a tile row.
+    // (channel passes — C > 128 fp32 — need the records again: no aliasing there; LPB != 0 implies a single pass)
+    // Only the eight-view instantiations do this: with four views the footprint fits the L1 that is left anyway and the
+    // stretched records cost 3 % (cfg2 290 -> 299 us).
+    const bool ALIAS = (OUT == 0 || OUT == 3) && VMAX > 4 && (LPB != 0 || p.alias);
+    // pitch = an ODD number of 16-byte units: the lanes' records in phase A and the lanes' rows in the read-out then
+    // spread over all banks without any swizzle
+    const int pitch = ALIAS ? (max(rec_bytes, nvec * 16) | 16) : rec_bytes;
+    const unsigned char *dummy = ALIAS ? recs + p.off_dummy : recs;
+    if (ALIAS) {
+        for (int i = lane; i < rec_bytes / 4; i += 32) reinterpret_cast<unsigned *>(recs + p.off_dummy)[i] = 0u;
+        __syncwarp();
+    }
 
     // OUT == 3: lane <-> joint (channel) for the whole launch.  The lane keeps ONE online-softmax record
     // over every voxel its warp produces for the current sample; it is flushed when the warp moves on
@@ -99,8 +117,16 @@ unproject_kernel(const UnprojParams p)
     // Tasks are dealt in chunks of p.ychunk consecutive y rows, chunk k to CTA k % gridDim.x:
     // all CTAs work on neighbouring chunks (one sample's maps stay in L2) and a CTA's
     // consecutive tasks share texel rows in L1.
+    // ... dealt DYNAMICALLY: the first gridDim.x chunks are pre-assigned, every further one is taken from a global
+    // counter (zeroed by the launcher).  Thread 0 asks for the CTA's next chunk while the current one is being
+    // worked on and publishes it through shared memory; the CTA meets once per chunk to read it.  SMs do not all
+    // run at the same speed (L2 distance): with a static deal the slowest of 148 set the time (+-10 % spread
+    // measured once the larger L1 made the kernel latency-bound).
     const unsigned nchunk = (p.ntasks + p.ychunk - 1) / p.ychunk;
-    for (unsigned ck = blockIdx.x; ck < nchunk; ck += gridDim.x) {
+    __shared__ unsigned s_deal[2];
+    unsigned deal_it = 0;
+    for (unsigned ck = blockIdx.x; ck < nchunk; ) {
+    if (p.deal && threadIdx.x == 0) s_deal[deal_it & 1] = gridDim.x + atomicAdd(p.deal, 1u);
     unsigned ct = ck * p.ychunk;
     const unsigned ct_end = min(p.ntasks, ct + p.ychunk);
     // task -> (b, z segment, x block, y): divisions once per chunk, then counted up
@@ -129,6 +155,14 @@ unproject_kernel(const UnprojParams p)
     const long long nme = nrow + lane;               // the voxel this lane projects / writes
     const bool mine = (lane < zn) && (nme >= p.n0) && (nme < p.n1);
 
+    // lane / steps by multiplication (exact for lane < 32, steps <= 32): the lane group that serves voxel `lane`
+    const unsigned zmagic = zn == p.lz ? p.magic_full : p.magic_last;
+    const unsigned g_of_lane = ((unsigned)lane * zmagic) >> 16;
+    // row z of the output tile (formats 0 / 3: over the record of voxel z, with its group's skew)
+    auto tile_row = [&](int z, unsigned g) -> float4 * {
+        return ALIAS ? reinterpret_cast<float4 *>(recs + z * pitch + g * 16) : tile + z * nvec;
+    };
+
     // ---- phase A: one voxel per lane, projected through every view ----
     if (lane < zn) {
         float X = 0.0f, Y = 0.0f, Z = 0.0f;
@@ -149,9 +183,7 @@ unproject_kernel(const UnprojParams p)
             Z = __fadd_rn(rot_row(__ldg(R + 6), __ldg(R + 7), __ldg(R + 8), d0, d1, d2), c2);
         }
         if (OUT == 3) sa_xyz[lane] = make_float4(1.0f, X, Y, Z);   // (1, x, y, z): the sums (S, X) and (Y, Z) advance as two packed FMAs
-        // lane / steps by multiplication (exact for lane < 32, steps <= 32)
-        const unsigned g_of_lane = ((unsigned)lane * (zn == p.lz ? p.magic_full : p.magic_last)) >> 16;
-        unsigned char *rec = recs + lane * rec_bytes + g_of_lane * 16;
+        unsigned char *rec = recs + lane * pitch + g_of_lane * 16;
         const float4 *Pb = reinterpret_cast<const float4 *>(p.proj + (size_t)b * p.V * 12);
         auto one_view = [&](int v) {
             const float4 P0 = __ldg(Pb + 3 * v), P1 = __ldg(Pb + 3 * v + 1), P2 = __ldg(Pb + 3 * v + 2);
@@ -240,22 +272,22 @@ unproject_kernel(const UnprojParams p)
                     }
                     *slot = val;
                 } else {
-                    tile[zl * nvec + (vec ^ (zl & (nvec - 1)))] = val;
+                    tile_row(zl, grp)[ALIAS ? vec : vec ^ (zl & (nvec - 1))] = val;
                 }
             }
         };
 
         // ---- phase B: each lane group walks its run of consecutive z voxels ----
-        const unsigned char *rec = recs + (grp * steps) * rec_bytes + grp * 16;
+        const unsigned char *rec = recs + (grp * steps) * pitch + grp * 16;
         int zl = grp * steps;
         const bool piped = single && CACHE && VMAX <= 4;   // the cached path software-pipelines its gathers
         if (piped) {
             // software pipeline: blend this voxel, issue the next voxel's gathers, then do the view
             // fusion (exp, sums) while those loads are in flight.  (Also prefetching the next
             // voxel's weights and the offsets after that costs registers and was slower.)
-            bool store_next = gather(zl < zn ? rec : recs, 0, p.V) && (zl < zn);
-            for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
-                const unsigned char *r = zl < zn ? rec : recs;
+            bool store_next = gather(zl < zn ? rec : dummy, 0, p.V) && (zl < zn);
+            for (int st = 0; st < steps; ++st, ++zl, rec += pitch) {
+                const unsigned char *r = zl < zn ? rec : dummy;
                 Fuse2<METHOD, VMAX, EXACT> fz[NP];
                 const bool store = store_next;
                 u64 s[VMAX][NP];
@@ -264,14 +296,14 @@ unproject_kernel(const UnprojParams p)
                     if (EXACT || v < p.V)
                         blend_texels<BF16>(s[v], tex[v][0], tex[v][1], tex[v][2], tex[v][3],
                                            reinterpret_cast<const float4 *>(r)[v]);
-                if (st + 1 < steps) store_next = gather(zl + 1 < zn ? rec + rec_bytes : recs, 0, p.V) && (zl + 1 < zn);
+                if (st + 1 < steps) store_next = gather(zl + 1 < zn ? rec + pitch : dummy, 0, p.V) && (zl + 1 < zn);
 #pragma unroll
                 for (int i = 0; i < NP; ++i) fz[i].absorb(&s[0][i], NP, p.V, true);
                 if (store) emit(zl, fz);
             }
         } else {
-            for (int st = 0; st < steps; ++st, ++zl, rec += rec_bytes) {
-                const unsigned char *r = zl < zn ? rec : recs;
+            for (int st = 0; st < steps; ++st, ++zl, rec += pitch) {
+                const unsigned char *r = zl < zn ? rec : dummy;
                 Fuse2<METHOD, VMAX, EXACT> fz[NP];
                 bool store = zl < zn;
                 for (int vb = 0; vb < p.V; vb += VMAX) {
@@ -305,23 +337,31 @@ unproject_kernel(const UnprojParams p)
         // window: every voxel of the task counts.)
         if (OUT == 3 && cb == 0) {
             const int c = min(lane, 4 * nvec - 1);
-            const float *tf = reinterpret_cast<const float *>(tile) + (c & 3);
             const int cv = c >> 2;
+            // word (z, c) of the tile: row z, vector cv swizzled by z
+            auto tile_word = [&](int z, unsigned g) -> float {
+                return reinterpret_cast<const float *>(tile_row(z, g))[((ALIAS ? cv : cv ^ (z & (nvec - 1))) << 2) + (c & 3)];
+            };
             constexpr int NVC = LPB ? (BF16 ? 2 : 1) * ((1 << LPB) / 16 < kVecPass ? (1 << LPB) / 16 : kVecPass) : 0;   // nvec, when known
-            constexpr int PER = NVC < 32 ? NVC : 32;                 // period of the row swizzle within a task
+            constexpr int SPG = NVC ? (BF16 ? NVC / 2 : NVC) : 1;    // steps per lane group of a full segment = lanes per voxel
             float mt = -FLT_MAX;
-            if (LPB != 0 && zn == kLzMax) {
-                // full segment, compile-time row size: rows z and z + PER share their swizzle, so the lane's
-                // word offset is computed PER times and every read carries an immediate offset
+            constexpr int PER = NVC < 32 ? NVC : 32;                 // period of the row swizzle of the separate tile
+            if (ALIAS && LPB != 0 && zn == kLzMax) {
+                // full segment, compile-time pitch: every read carries an immediate offset
+                const float *t = reinterpret_cast<const float *>(recs) + c;
+#pragma unroll
+                for (int z = 0; z < kLzMax; ++z) mt = fmaxf(mt, t[(z * pitch + (z / SPG) * 16) >> 2]);
+            } else if (LPB != 0 && zn == kLzMax) {
+                // separate tile: rows z and z + PER share their swizzle, so the lane's word offset is computed PER times
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
-                    const float *t = tf + ((cv ^ k) << 2);
+                    const float *t = reinterpret_cast<const float *>(tile) + ((cv ^ k) << 2) + (c & 3);
 #pragma unroll
                     for (int z = k; z < kLzMax; z += PER) mt = fmaxf(mt, t[z * NVC * 4]);
                 }
             } else {
 #pragma unroll 4
-                for (int z = 0; z < zn; ++z) mt = fmaxf(mt, tf[(z * nvec + (cv ^ (z & (nvec - 1)))) << 2]);
+                for (int z = 0; z < zn; ++z) mt = fmaxf(mt, tile_word(z, ((unsigned)z * zmagic) >> 16));
             }
             const float mn = fmaxf(sa_m, mt);
             const float r = ex2_approx((sa_m - mn) * kLog2e);        // 1 if the max stands, 0 for the first task
@@ -335,16 +375,20 @@ unproject_kernel(const UnprojParams p)
                 sa_SX = fma2(ee, pk(c1.x, c1.y), sa_SX);
                 sa_YZ = fma2(ee, pk(c1.z, c1.w), sa_YZ);
             };
-            if (LPB != 0 && zn == kLzMax) {
+            if (ALIAS && LPB != 0 && zn == kLzMax) {
+                const float *t = reinterpret_cast<const float *>(recs) + c;
+#pragma unroll
+                for (int z = 0; z < kLzMax; ++z) absorb_voxel(t[(z * pitch + (z / SPG) * 16) >> 2], z);
+            } else if (LPB != 0 && zn == kLzMax) {
 #pragma unroll
                 for (int k = 0; k < PER; ++k) {
-                    const float *t = tf + ((cv ^ k) << 2);
+                    const float *t = reinterpret_cast<const float *>(tile) + ((cv ^ k) << 2) + (c & 3);
 #pragma unroll
                     for (int z = k; z < kLzMax; z += PER) absorb_voxel(t[z * NVC * 4], z);
                 }
             } else {
 #pragma unroll 4
-                for (int z = 0; z < zn; ++z) absorb_voxel(tf[(z * nvec + (cv ^ (z & (nvec - 1)))) << 2], z);
+                for (int z = 0; z < zn; ++z) absorb_voxel(tile_word(z, ((unsigned)z * zmagic) >> 16), z);
             }
         }
         // ---- read out: lane <-> voxel, one coalesced 128-byte store per channel ----
@@ -357,8 +401,8 @@ unproject_kernel(const UnprojParams p)
                                         : nme - p.n_origin;
             const size_t cs = (size_t)p.n_extent_out;
             float *o = p.out + ((size_t)b * p.C + c_base) * cs + (mine_o ? vo : 0);
-            const float4 *trow = tile + zr * nvec;
-            const int sw = zr & (nvec - 1);
+            const float4 *trow = tile_row(zr, mine_o ? g_of_lane : 0u);
+            const int sw = ALIAS ? 0 : zr & (nvec - 1);
             const int kfull = min(nvec, (p.C - c_base) >> 2);        // vectors with all four channels present
             int k = 0;
             for (; k < kfull; ++k, o += 4 * cs) {
@@ -379,6 +423,13 @@ unproject_kernel(const UnprojParams p)
     }
     }   // sub-rows of a pooled task (the task body)
     }   // tasks of one chunk
+    if (p.deal) {
+        __syncthreads();
+        ck = s_deal[deal_it & 1];
+        ++deal_it;
+    } else {
+        ck += gridDim.x;                             // static round-robin: the warps never meet
+    }
     }   // persistent chunk loop
     if (OUT == 3) sa_flush();
 }
