@@ -34,6 +34,8 @@ def summary(rep_name, cmd, dst, note=''):
                     f.write('%s = %s\n' % (k, d[k]))
             f.write('\n')
     print(open(os.path.join(PR, dst)).read())
+    d = dict(zip(hdr, rows[-1])); d['__units__'] = dict(zip(hdr, rows[1]))
+    return d
 
 
 def launch_shares(src_name, dst_csv, dst_txt, header):
@@ -67,6 +69,10 @@ summary('prof_r2_tex_v1_cfg3.ncu-rep',
         'ncu --set full --clock-control none --import-source on -k regex:unproject_tex -s 2 -c 1 python scripts/prof_fast.py cfg3',
         'r2_tex_path_v1_cfg3_ncu_full_summary.txt',
         "(precision='fast', the committed texture-path kernel: plain-FMA position, 16 z x 2 x lane mapping; XU = MUFU is the busiest pipe)\n")
+d5 = summary('prof_r2b_cfg5_full.ncu-rep',
+        'ncu --set full --clock-control none --import-source on -k regex:unproject_kernel -s 2 -c 1 python scripts/prof_run.py cfg5 3   (B = 64: the headline launch)',
+        'r2_unproject_cfg5_v2_ncu_full_summary.txt',
+        '(the headline kernel after the output tile moved into the records and the CTA chunks are dealt dynamically; the earlier state is r2_unproject_cfg5_ncu_full_summary.txt)\n')
 launch_shares('r2b_bench_launches.csv', 'r2_bench_launches.csv', 'r2_bench_launch_shares.txt',
               'ncu --metrics gpu__time_duration.sum --clock-control none -c 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline\n'
               '(cold-cache, serialised launches: shares, not absolutes; the first 600 launches cover the headline loop, both e2e legs and the start of the per-config block)\n')
@@ -74,3 +80,15 @@ for src, dst in (('r2b_bench_final.json', 'r2_bench_line.json'), ('r2b_bench_n2.
     p = os.path.join(GO, src)
     if os.path.exists(p):
         open(os.path.join(PR, dst), 'w').write(open(p).read().strip().splitlines()[-1] + '\n')
+
+if d5:
+    import json
+    scale = {'Mbyte': 1e6, 'Gbyte': 1e9, 'Kbyte': 1e3, 'byte': 1}
+    u = d5['__units__']
+    rd = float(d5['dram__bytes_read.sum']) * scale[u['dram__bytes_read.sum']]
+    wr = float(d5['dram__bytes_write.sum']) * scale[u['dram__bytes_write.sum']]
+    tp = os.path.join(PR, 'traffic.json')
+    traffic = json.load(open(tp))
+    traffic['cfg5'] = int(rd + wr); traffic['cfg5_read'] = int(rd); traffic['cfg5_write'] = int(wr)
+    json.dump(traffic, open(tp, 'w'), indent=1)
+    print('traffic cfg5', traffic['cfg5'])
