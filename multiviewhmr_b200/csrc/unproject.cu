@@ -526,7 +526,22 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
         }
     }
     if (const char *env = getenv("MVHMR_YCHUNK")) { const int v = atoi(env); if (v >= 1) p.ychunk = (unsigned)v; }   // tuning knob
-    const unsigned nchunk = (unsigned)((ntasks + p.ychunk - 1) / p.ychunk);
+    // dynamic deal: the last ~one-and-a-half chunks' worth of work per CTA goes out in single tasks (cfg5 at 8 samples per
+    // GPU: the tail of an 8-row chunk is up to 130 us of a 1 ms launch)
+    p.ytail = 1;
+    {
+        const long long all_big = (ntasks + p.ychunk - 1) / p.ychunk;
+        long long nbig = all_big;
+        if (dynamic_deal && p.ychunk > 1 && !getenv("MVHMR_NO_TAIL")) {
+            nbig = (ntasks - 3ll * resident * p.ychunk / 2) / p.ychunk;
+            if (nbig < 0) nbig = 0;
+        }
+        p.nbig = (unsigned)nbig;
+        const long long rest = ntasks - nbig * (long long)p.ychunk;
+        p.nchunk = (unsigned)(nbig + (nbig == all_big ? 0 : (rest + p.ytail - 1) / p.ytail));
+        if (nbig == all_big) p.nbig = p.nchunk;                  // uniform chunks: every index takes the first branch
+    }
+    const unsigned nchunk = p.nchunk;
     const dim3 grid(nchunk < resident ? nchunk : resident);
     p.deal = dynamic_deal ? deal_slot(st) : nullptr;                 // NULL: static round-robin (also when no slot could be had)
     const unsigned g = grid.x;

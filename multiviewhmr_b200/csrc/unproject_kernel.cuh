@@ -122,13 +122,14 @@ unproject_kernel(const UnprojParams p)
     // worked on and publishes it through shared memory; the CTA meets once per chunk to read it.  SMs do not all
     // run at the same speed (L2 distance): with a static deal the slowest of 148 set the time (+-10 % spread
     // measured once the larger L1 made the kernel latency-bound).
-    const unsigned nchunk = (p.ntasks + p.ychunk - 1) / p.ychunk;
+    const unsigned nchunk = p.nchunk;
     __shared__ unsigned s_deal[2];
     unsigned deal_it = 0;
     for (unsigned ck = blockIdx.x; ck < nchunk; ) {
     if (p.deal && threadIdx.x == 0) s_deal[deal_it & 1] = gridDim.x + atomicAdd(p.deal, 1u);
-    unsigned ct = ck * p.ychunk;
-    const unsigned ct_end = min(p.ntasks, ct + p.ychunk);
+    // the last chunks of a dynamic deal are short ones (p.ytail tasks), so that the CTAs finish within a task or two of each other
+    unsigned ct = ck < p.nbig ? ck * p.ychunk : p.nbig * p.ychunk + (ck - p.nbig) * p.ytail;
+    const unsigned ct_end = min(p.ntasks, ct + (ck < p.nbig ? p.ychunk : p.ytail));
     // task -> (b, z segment, x block, y): divisions once per chunk, then counted up
     unsigned t = ct / (unsigned)p.ty;
     int vy = (int)(ct - t * (unsigned)p.ty);
