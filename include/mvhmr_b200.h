@@ -13,7 +13,10 @@
  *   - Plain pointers and sizes only.  All `const float*` / `void*` data
  *     pointers are DEVICE pointers on the current CUDA device unless a
  *     parameter says "host".  The caller owns every buffer; the library
- *     allocates nothing and keeps no state between calls.
+ *     allocates nothing and keeps no state between calls (two bounded
+ *     scratch tables aside: texture-object descriptors of the caller's
+ *     workspace, and a 4 KB ring of per-launch work counters in the
+ *     library's own device data, zeroed on the caller's stream before use).
  *   - Every call is asynchronous on `stream` (a cudaStream_t passed as
  *     void*; NULL = legacy default stream), does no host synchronisation and
  *     no allocation, and is CUDA-graph capturable.
