@@ -112,16 +112,17 @@ unproject_kernel(const UnprojParams p)
 
     // Persistent CTAs.  A CTA task = kWarps consecutive x planes of one (sample, z segment, y)
     // row, one plane per warp: their projections overlap almost completely in every view, so the
-    // CTA's texel footprint stays L1-resident.  Warps are never synchronised with each other and
-    // drift apart in phase (projection / gathers / stores of different warps overlap).
-    // Tasks are dealt in chunks of p.ychunk consecutive y rows, chunk k to CTA k % gridDim.x:
-    // all CTAs work on neighbouring chunks (one sample's maps stay in L2) and a CTA's
-    // consecutive tasks share texel rows in L1.
-    // ... dealt DYNAMICALLY: the first gridDim.x chunks are pre-assigned, every further one is taken from a global
-    // counter (zeroed by the launcher).  Thread 0 asks for the CTA's next chunk while the current one is being
-    // worked on and publishes it through shared memory; the CTA meets once per chunk to read it.  SMs do not all
-    // run at the same speed (L2 distance): with a static deal the slowest of 148 set the time (+-10 % spread
-    // measured once the larger L1 made the kernel latency-bound).
+    // CTA's texel footprint stays L1-resident.  Within a chunk the warps are never synchronised with each
+    // other and drift apart in phase (projection / gathers / stores of different warps overlap).
+    // Tasks are dealt in chunks of p.ychunk consecutive y rows: all CTAs work on neighbouring chunks (one
+    // sample's maps stay in L2) and a CTA's consecutive tasks share texel rows in L1.
+    //  * p.deal == NULL (four-view and fused soft-argmax kernels): statically, chunk k to CTA k % gridDim.x;
+    //    the warps never meet at all.
+    //  * p.deal != NULL (eight-view kernels): DYNAMICALLY — the first gridDim.x chunks are pre-assigned, every
+    //    further one is taken from a global counter (zeroed by the launcher).  Thread 0 asks for the CTA's next
+    //    chunk while the current one is being worked on and publishes it through shared memory; the CTA meets
+    //    once per chunk to read it.  SMs do not all run at the same speed (L2 distance): with a static deal the
+    //    slowest of 148 sets the time (+-10 % spread once the larger L1 made these kernels latency-bound).
     const unsigned nchunk = p.nchunk;
     __shared__ unsigned s_deal[2];
     unsigned deal_it = 0;
