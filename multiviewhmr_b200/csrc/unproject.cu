@@ -17,15 +17,19 @@
 //     voxels and keeps the four corner texels of every view in registers: when
 //     the next voxel projects into the same bilinear cell (views looking along
 //     z move ~0.3 px per voxel) nothing is loaded at all.
-//   * Phase A (once per warp task = one z segment of <= 64 voxels): every lane
-//     projects up to two voxels through every view with IEEE ops in the
+//   * Phase A (once per warp task = one z segment of <= 32 voxels): every lane
+//     projects one voxel through every view with IEEE ops in the
 //     reference's order and parks (pixel offset, 4 weights) in shared memory,
 //     so the projection is never recomputed per channel.  Phase B: the walk.
 //     Blend = mul + 3 FMA per channel issued as packed FFMA2; view fusion in
 //     registers (softmax: one FFMA2 for two exp arguments, MUFU.EX2).
-//   * Results are transposed through a swizzled shared-memory tile so that each
-//     warp writes full 128-byte lines of the (B,C,N) output; every output value
-//     is written exactly once and no per-view volume exists anywhere.
+//   * Results are transposed through a shared-memory tile so that each warp
+//     writes full 128-byte lines of the (B,C,N) output; every output value is
+//     written exactly once and no per-view volume exists anywhere.  The eight-view
+//     kernels keep that tile INSIDE the voxel records (a record is dead once its
+//     voxel is done), which leaves 64 KB more L1 per SM for the texel footprint,
+//     and take their work from a per-launch counter (the host code below picks
+//     segment lengths, chunk lengths and the way chunks are dealt).
 #include <cuda_bf16.h>
 #include <cstdlib>
 #include <atomic>
