@@ -277,15 +277,17 @@ static std::atomic<unsigned> g_deal_ticket{0};
 
 static unsigned *deal_slot(cudaStream_t st)
 {
-    static unsigned *base[64] = {};
+    static std::atomic<unsigned *> base[64];         // per device; concurrent first calls store the same address
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-    if (!base[dev]) {
+    unsigned *ring = base[dev].load(std::memory_order_acquire);
+    if (!ring) {
         void *ptr = nullptr;
         if (cudaGetSymbolAddress(&ptr, g_deal_ring) != cudaSuccess) return nullptr;
-        base[dev] = (unsigned *)ptr;
+        ring = (unsigned *)ptr;
+        base[dev].store(ring, std::memory_order_release);
     }
-    unsigned *slot = base[dev] + (g_deal_ticket.fetch_add(1u) & 1023u);
+    unsigned *slot = ring + (g_deal_ticket.fetch_add(1u) & 1023u);
     if (cudaMemsetAsync(slot, 0, sizeof(unsigned), st) != cudaSuccess) return nullptr;
     return slot;
 }
@@ -402,7 +404,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     for (;;) {                                                      // a hint that does not fit is shortened
         off_tile = (lz * rec_pitch + (32 / nch_pass) * 16 + 15) & ~15;  // + per-group skew
         warp_smem = off_tile + lz * tile_row + dummy_bytes + (sa ? kLzMax * 16 : 0);   // (+ dummy record) (+ the task's voxel coordinates)
-        if (const char *env = getenv("MVHMR_SMEM_PAD")) warp_smem += atoi(env) & ~15;   // experiment: unused bytes per warp
+        if (const char *env = getenv("MVHMR_SMEM_PAD")) { const int v = atoi(env); if (v > 0 && v <= 8192) warp_smem += v & ~15; }   // tuning knob: unused bytes per warp (moves the L1 / shared-memory carve-out)
         smem = (size_t)warp_smem * kWarps;
         if (smem <= smem_cap || lz == 1 || (pool && lz == 2)) break;
         lz = (lz + 1) / 2;
