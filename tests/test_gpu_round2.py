@@ -411,3 +411,38 @@ def test_task_chunking_does_not_change_results(monkeypatch, V):
     for yc in ("1", "3", "5", "7", "16", "1000"):
         monkeypatch.setenv("MVHMR_YCHUNK", yc)
         assert torch.equal(agg.unprojection(fd, Pd, cvd, "softmax"), ref), yc
+
+
+def test_eight_view_launches_on_concurrent_streams_and_threads():
+    """The eight-view kernels take their work from a per-launch counter inside the library (a ring of slots):
+    launches in flight at the same time — several streams, several host threads — must not share one."""
+    import threading
+    w = syn.Workload("t", B=2, V=8, C=32, H=48, W=48, G=40)
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    ref = agg.unprojection(fd, Pd, cvd, "softmax")
+    packed = agg.pack_features(fd)
+    torch.cuda.synchronize()
+    results, errors = {}, []
+
+    def worker(k):
+        try:
+            st = torch.cuda.Stream()
+            outs = []
+            with torch.cuda.stream(st):
+                for _ in range(6):
+                    outs.append(agg.unprojection(fd, Pd, cvd, "softmax", packed=packed))
+            st.synchronize()
+            results[k] = outs
+        except Exception as exc:          # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(k,)) for k in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for outs in results.values():
+        for o in outs:
+            assert torch.equal(o, ref)
