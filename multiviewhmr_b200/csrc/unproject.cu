@@ -515,6 +515,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     //    (scripts/ychunk_sweep.py).  The fused soft-argmax format is dealt statically too: its records would
     //    otherwise be summed in a different order from run to run.
     const bool dynamic_deal = V > 4 && !sa && !getenv("MVHMR_STATIC_DEAL");
+    const bool use_counter = dynamic_deal || (!sa && getenv("MVHMR_DYN_ROUNDS"));     // four-view kernels: only as an experiment
     if (dynamic_deal) {
         p.ychunk = 8;
         while (p.ychunk > 1 && ntasks / p.ychunk < 8ll * resident) p.ychunk >>= 1;
@@ -538,7 +539,7 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     {
         const long long all_big = (ntasks + p.ychunk - 1) / p.ychunk;
         long long nbig = all_big;
-        if (dynamic_deal && p.ychunk > 1 && !getenv("MVHMR_NO_TAIL")) {
+        if (use_counter && p.ychunk > 1 && !getenv("MVHMR_NO_TAIL")) {
             nbig = (ntasks - 3ll * resident * p.ychunk / 2) / p.ychunk;
             if (nbig < 0) nbig = 0;
         }
@@ -549,8 +550,19 @@ static int unproject_impl(const void *feats, int feat_dtype, int feat_layout,
     }
     const unsigned nchunk = p.nchunk;
     const dim3 grid(nchunk < resident ? nchunk : resident);
-    p.deal = dynamic_deal ? deal_slot(st) : nullptr;                 // NULL: static round-robin (also when no slot could be had)
     const unsigned g = grid.x;
+    // Four-view kernels stay on the static deal: handing even only the last round or two over the counter
+    // (MVHMR_DYN_ROUNDS=<n>, the rounds before them static) to even out the finish — the average SM idles 5 % of a cfg2
+    // launch — costs more than it recovers (cfg2 289.8 us static, 293.8 / 295.4 / 295.8 us with 1 / 2 / 3 dynamic rounds).
+    p.deal = use_counter ? deal_slot(st) : nullptr;                  // NULL: static round-robin (also when no slot could be had)
+    {
+        const long long rounds = nchunk / g;
+        long long static_rounds = dynamic_deal ? 1 : rounds - 2;
+        if (const char *env = getenv("MVHMR_DYN_ROUNDS")) static_rounds = rounds - atoi(env);        // tuning knob
+        if (static_rounds < 1) static_rounds = 1;
+        p.nstatic = (unsigned)(static_rounds * g < nchunk ? static_rounds * g : nchunk);
+        if (p.nstatic < g) p.nstatic = g;                            // the first round is always pre-assigned (ck = blockIdx.x)
+    }
     if (sa) {
         // one record per (sample, joint, CTA, warp); slots a warp never reaches stay zero (= empty for the merge)
         const size_t need = (size_t)B * sa_J * g * kWarps * 5 * sizeof(float);

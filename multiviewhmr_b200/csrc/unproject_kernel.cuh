@@ -116,10 +116,11 @@ unproject_kernel(const UnprojParams p)
     // other and drift apart in phase (projection / gathers / stores of different warps overlap).
     // Tasks are dealt in chunks of p.ychunk consecutive y rows: all CTAs work on neighbouring chunks (one
     // sample's maps stay in L2) and a CTA's consecutive tasks share texel rows in L1.
-    //  * p.deal == NULL (four-view and fused soft-argmax kernels): statically, chunk k to CTA k % gridDim.x;
-    //    the warps never meet at all.
-    //  * p.deal != NULL (eight-view kernels): DYNAMICALLY — the first gridDim.x chunks are pre-assigned, every
-    //    further one is taken from a global counter (zeroed by the launcher).  Thread 0 asks for the CTA's next
+    //  * p.deal == NULL (four-view and fused soft-argmax kernels): statically, chunk k to CTA k % gridDim.x; the warps never
+    //    meet at all.
+    //  * p.deal != NULL (eight-view kernels): the first p.nstatic chunks statically (one round: the pre-assigned
+    //    ck = blockIdx.x), every further one DYNAMICALLY from a global counter (zeroed by the launcher).  (Four-view
+    //    kernels pay 5-7 % for meeting once per chunk and stay static: p.deal == NULL.)  Thread 0 asks for the CTA's next
     //    chunk while the current one is being worked on and publishes it through shared memory; the CTA meets
     //    once per chunk to read it.  SMs do not all run at the same speed (L2 distance): with a static deal the
     //    slowest of 148 sets the time (+-10 % spread once the larger L1 made these kernels latency-bound).
@@ -127,7 +128,9 @@ unproject_kernel(const UnprojParams p)
     __shared__ unsigned s_deal[2];
     unsigned deal_it = 0;
     for (unsigned ck = blockIdx.x; ck < nchunk; ) {
-    if (p.deal && threadIdx.x == 0) s_deal[deal_it & 1] = gridDim.x + atomicAdd(p.deal, 1u);
+    // round-robin while the CTA's next chunk is still a static one; from its last static chunk on, the counter
+    const bool handover = p.deal && ck + gridDim.x >= p.nstatic;
+    if (handover && threadIdx.x == 0) s_deal[deal_it & 1] = p.nstatic + atomicAdd(p.deal, 1u);
     // the last chunks of a dynamic deal are short ones (p.ytail tasks), so that the CTAs finish within a task or two of each other
     unsigned ct = ck < p.nbig ? ck * p.ychunk : p.nbig * p.ychunk + (ck - p.nbig) * p.ytail;
     const unsigned ct_end = min(p.ntasks, ct + (ck < p.nbig ? p.ychunk : p.ytail));
@@ -425,12 +428,12 @@ unproject_kernel(const UnprojParams p)
     }
     }   // sub-rows of a pooled task (the task body)
     }   // tasks of one chunk
-    if (p.deal) {
+    if (handover) {
         __syncthreads();
         ck = s_deal[deal_it & 1];
         ++deal_it;
     } else {
-        ck += gridDim.x;                             // static round-robin: the warps never meet
+        ck += gridDim.x;                             // static round-robin: the warps do not meet
     }
     }   // persistent chunk loop
     if (OUT == 3) sa_flush();
