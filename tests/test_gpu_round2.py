@@ -446,3 +446,23 @@ def test_eight_view_launches_on_concurrent_streams_and_threads():
     for outs in results.values():
         for o in outs:
             assert torch.equal(o, ref)
+
+
+def test_eight_view_launch_replayed_from_a_cuda_graph():
+    """The work counter of an eight-view launch is zeroed by a memset node captured in front of the kernel: a graph
+    replays to the same bits every time."""
+    w = syn.Workload("t", B=2, V=8, C=32, H=48, W=48, G=40)
+    f, P, cv, _ = syn.make_inputs(w)
+    fd, Pd, cvd = cuda(f, P, cv)
+    ref = agg.unprojection(fd, Pd, cvd, "softmax")
+    packed = agg.pack_features(fd)
+    out = torch.empty_like(ref)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        agg.unprojection(fd, Pd, cvd, "softmax", packed=packed, out=out)
+    for _ in range(3):
+        out.fill_(float("nan"))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
